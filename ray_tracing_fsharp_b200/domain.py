@@ -1,0 +1,349 @@
+"""Host-side mirror of the reference's scene-description API (names follow the F# modules).
+
+The reference's toolchain (.NET / F#) is absent from this image, so the host surface that would
+stay in F# (`Scene/Hittable/Camera/Texture`) is mirrored here in Python, one class
+per F# type, with the same names and argument meaning, so that tests read like the reference's.
+Everything here is plain data; `marshal()` flattens a Hittable list into the C-ABI arrays
+(include/rtfs_b200.h) exactly as the F# shim (shim/RayTracing.Gpu.fs) would.
+
+Reference types mirrored:
+  Pixel, Colour                     RayTracing/Pixel.fs:9-76
+  Texture, ParameterisedTexture     RayTracing/Texture.fs:5-72
+  SphereStyle, Sphere               RayTracing/Sphere.fs:10-37, :302-337
+  InfinitePlaneStyle, InfinitePlane RayTracing/InfinitePlane.fs:3-13, :101-119
+  Hittable                          RayTracing/Hittable.fs:3-6
+"""
+from dataclasses import dataclass, field
+from typing import Any, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import abi
+
+
+# ---- Pixel.fs -------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class Pixel:
+    Red: int
+    Green: int
+    Blue: int
+
+    def __post_init__(self):
+        for c in (self.Red, self.Green, self.Blue):
+            if not (0 <= int(c) <= 255):
+                raise ValueError("Pixel channels are bytes")
+
+    def as_tuple(self):
+        return (int(self.Red), int(self.Green), int(self.Blue))
+
+
+class Colour:
+    Black = Pixel(0, 0, 0)
+    White = Pixel(255, 255, 255)
+    Red = Pixel(255, 0, 0)
+    Green = Pixel(0, 255, 0)
+    Blue = Pixel(0, 0, 255)
+    Yellow = Pixel(255, 255, 0)
+    HotPink = Pixel(205, 105, 180)
+
+    @staticmethod
+    def random(rand: np.random.Generator) -> Pixel:
+        b = rand.integers(0, 256, size=3)
+        return Pixel(int(b[0]), int(b[1]), int(b[2]))
+
+
+# ---- Texture.fs -----------------------------------------------------------------------------
+@dataclass(frozen=True)
+class PlaneMapInverse:
+    """The `interpret` closure `Sphere.planeMapInverse radius centre` (Sphere.fs:55-61) as data."""
+    radius: float
+    centre: Tuple[float, float, float]
+
+
+class ParameterisedTexture:
+    @dataclass(frozen=True)
+    class Colour:
+        pixel: Pixel
+
+    @dataclass(frozen=True)
+    class Checkered:
+        even: Any
+        odd: Any
+        grid_size: float
+
+    @dataclass(frozen=True, eq=False)
+    class Image:
+        """`Pixel[][]` as ParameterisedTexture.Image holds it: img[y][x], uint8 array [H, W, 3]."""
+        img: np.ndarray
+
+    @staticmethod
+    def of_image(bitmap: np.ndarray) -> "ParameterisedTexture.Image":
+        """ParameterisedTexture.ofImage (Texture.fs:30-48): `bitmap` is [H, W, 3] with row 0 the
+        top row of the picture (what SKBitmap.GetPixel(x, y) indexes); rows are flipped."""
+        b = np.ascontiguousarray(bitmap, dtype=np.uint8)
+        if b.ndim != 3 or b.shape[2] != 3:
+            raise ValueError("bitmap must be [H, W, 3] uint8")
+        return ParameterisedTexture.Image(np.ascontiguousarray(b[::-1]))
+
+    @staticmethod
+    def to_texture(interpret: PlaneMapInverse, texture) -> "Texture":
+        """ParameterisedTexture.toTexture (Texture.fs:69-72) — keeps the structure instead of
+        erasing it to a closure (F14), because a closure cannot cross the ABI."""
+        if isinstance(texture, ParameterisedTexture.Colour):
+            return Texture.Colour(texture.pixel)
+        if not isinstance(interpret, PlaneMapInverse):
+            raise TypeError("interpret must be Sphere.plane_map_inverse(radius, centre)")
+        return Texture.Parameterised(interpret, texture)
+
+
+class Texture:
+    @dataclass(frozen=True)
+    class Colour:
+        pixel: Pixel
+
+    @dataclass(frozen=True, eq=False)
+    class Parameterised:
+        interpret: PlaneMapInverse
+        texture: Any
+
+    @dataclass(frozen=True, eq=False)
+    class Arbitrary:
+        """Texture.Arbitrary (Point -> Pixel): a host closure.  Not executable on the device;
+        Scene.make raises (RT_ERR_UNSUPPORTED semantics) rather than mis-rendering."""
+        f: Any
+
+
+# ---- Sphere.fs ------------------------------------------------------------------------------
+class SphereStyle:
+    @dataclass(frozen=True)
+    class LightSource:
+        texture: Any
+
+    @dataclass(frozen=True)
+    class LightSourceCap:
+        colour: Pixel
+
+    @dataclass(frozen=True)
+    class PureReflection:
+        albedo: float
+        texture: Any
+
+    @dataclass(frozen=True)
+    class FuzzedReflection:
+        albedo: float
+        texture: Any
+        fuzz: float
+        rand: Any = None  # FloatProducer in the reference; the device RNG is keyed per pixel instead
+
+    @dataclass(frozen=True)
+    class LambertReflection:
+        albedo: float
+        texture: Any
+        rand: Any = None
+
+    @dataclass(frozen=True)
+    class Dielectric:
+        albedo: float
+        texture: Any
+        boundaryRefractance: float
+        refraction: float
+        rand: Any = None
+
+    @dataclass(frozen=True)
+    class Glass:
+        albedo: float
+        texture: Any
+        ior: float
+        rand: Any = None
+
+
+@dataclass(frozen=True)
+class Sphere:
+    Style: Any
+    Centre: Tuple[float, float, float]
+    Radius: float
+
+    @staticmethod
+    def make(style, centre, radius) -> "Sphere":
+        c = tuple(float(x) for x in centre)
+        if len(c) != 3:
+            raise ValueError("centre must have 3 coordinates")
+        return Sphere(style, c, float(radius))
+
+    @staticmethod
+    def plane_map_inverse(radius, centre) -> PlaneMapInverse:
+        return PlaneMapInverse(float(radius), tuple(float(x) for x in centre))
+
+
+# ---- InfinitePlane.fs -------------------------------------------------------------------------
+class InfinitePlaneStyle:
+    @dataclass(frozen=True)
+    class LightSource:
+        texture: Any
+
+    @dataclass(frozen=True)
+    class PureReflection:
+        albedo: float
+        colour: Pixel
+
+    @dataclass(frozen=True)
+    class LambertReflection:
+        albedo: float
+        colour: Pixel
+        rand: Any = None
+
+    @dataclass(frozen=True)
+    class FuzzedReflection:
+        albedo: float
+        colour: Pixel
+        fuzz: float
+        rand: Any = None
+
+
+@dataclass(frozen=True)
+class InfinitePlane:
+    Style: Any
+    Point: Tuple[float, float, float]
+    Normal: Tuple[float, float, float]
+
+    @staticmethod
+    def make(style, point_on_plane, normal) -> "InfinitePlane":
+        """InfinitePlane.make (InfinitePlane.fs:114-119).  `normal` must be a UnitVector."""
+        n = np.asarray(normal, dtype=np.float64)
+        if n.shape != (3,) or abs(float(n @ n) - 1.0) > 1e-6:
+            raise ValueError("normal must be a unit vector (UnitVector in the reference)")
+        return InfinitePlane(style, tuple(float(x) for x in point_on_plane), tuple(float(x) for x in n))
+
+
+# ---- Hittable.fs ------------------------------------------------------------------------------
+class Hittable:
+    @dataclass(frozen=True)
+    class Sphere:
+        sphere: Sphere
+
+    @dataclass(frozen=True)
+    class UnboundedSphere:
+        sphere: Sphere
+
+    @dataclass(frozen=True)
+    class InfinitePlane:
+        plane: InfinitePlane
+
+
+# ---- marshalling into the C ABI ----------------------------------------------------------------
+class _TextureTable:
+    def __init__(self):
+        self.entries: List[abi.RtTexture] = []
+        self.keep: List[np.ndarray] = []
+
+    def add_param(self, interpret: PlaneMapInverse, t) -> int:
+        e = abi.RtTexture()
+        e.even = e.odd = -1
+        e.map_centre[:] = interpret.centre
+        e.map_radius = interpret.radius
+        if isinstance(t, ParameterisedTexture.Colour):
+            e.kind = abi.RT_TEX_COLOUR
+            e.colour[:] = t.pixel.as_tuple()
+        elif isinstance(t, ParameterisedTexture.Image):
+            img = np.ascontiguousarray(t.img, dtype=np.uint8)
+            self.keep.append(img)
+            e.kind = abi.RT_TEX_IMAGE
+            e.height, e.width = img.shape[0], img.shape[1]
+            import ctypes as C
+            e.rgb8 = img.ctypes.data_as(C.POINTER(C.c_uint8))
+        elif isinstance(t, ParameterisedTexture.Checkered):
+            ev = self.add_param(interpret, t.even)
+            od = self.add_param(interpret, t.odd)
+            e.kind = abi.RT_TEX_CHECKERED
+            e.even, e.odd = ev, od
+            e.grid_size = float(t.grid_size)
+        else:
+            raise NotImplementedError(
+                "ParameterisedTexture.Arbitrary is a host closure and cannot be evaluated on the device "
+                "(RT_ERR_UNSUPPORTED); bake it to an Image first")
+        self.entries.append(e)
+        return len(self.entries) - 1
+
+
+def _set_texture(h: abi.RtHittable, tex, table: _TextureTable):
+    if isinstance(tex, Texture.Colour):
+        h.texture = -1
+        h.colour[:] = tex.pixel.as_tuple()
+    elif isinstance(tex, Pixel):
+        h.texture = -1
+        h.colour[:] = tex.as_tuple()
+    elif isinstance(tex, Texture.Parameterised):
+        h.texture = table.add_param(tex.interpret, tex.texture)
+    else:
+        raise NotImplementedError(
+            "Texture.Arbitrary is a host closure and cannot be evaluated on the device (RT_ERR_UNSUPPORTED)")
+
+
+def marshal(objects: Sequence[Any]):
+    """Hittable array -> (list[RtHittable], list[RtTexture], keepalive)."""
+    table = _TextureTable()
+    out = []
+    for obj in objects:
+        h = abi.RtHittable()
+        h.texture = -1
+        if isinstance(obj, (Hittable.Sphere, Hittable.UnboundedSphere)):
+            s = obj.sphere
+            h.shape = abi.RT_SHAPE_SPHERE if isinstance(obj, Hittable.Sphere) else abi.RT_SHAPE_UNBOUNDED_SPHERE
+            h.p[:] = s.Centre
+            h.radius = s.Radius
+            st = s.Style
+            if isinstance(st, SphereStyle.LightSource):
+                h.style = abi.RT_STYLE_LIGHT_SOURCE
+                _set_texture(h, st.texture, table)
+            elif isinstance(st, SphereStyle.LightSourceCap):
+                h.style = abi.RT_STYLE_LIGHT_SOURCE_CAP
+                h.colour[:] = st.colour.as_tuple()
+            elif isinstance(st, SphereStyle.PureReflection):
+                h.style = abi.RT_STYLE_PURE_REFLECTION
+                h.albedo = st.albedo
+                _set_texture(h, st.texture, table)
+            elif isinstance(st, SphereStyle.FuzzedReflection):
+                h.style = abi.RT_STYLE_FUZZED_REFLECTION
+                h.albedo, h.fuzz = st.albedo, st.fuzz
+                _set_texture(h, st.texture, table)
+            elif isinstance(st, SphereStyle.LambertReflection):
+                h.style = abi.RT_STYLE_LAMBERT_REFLECTION
+                h.albedo = st.albedo
+                _set_texture(h, st.texture, table)
+            elif isinstance(st, SphereStyle.Dielectric):
+                h.style = abi.RT_STYLE_DIELECTRIC
+                h.albedo, h.ior, h.prob = st.albedo, st.boundaryRefractance, st.refraction
+                _set_texture(h, st.texture, table)
+            elif isinstance(st, SphereStyle.Glass):
+                h.style = abi.RT_STYLE_GLASS
+                h.albedo, h.ior = st.albedo, st.ior
+                _set_texture(h, st.texture, table)
+            else:
+                raise TypeError(f"unknown SphereStyle {st!r}")
+        elif isinstance(obj, Hittable.InfinitePlane):
+            p = obj.plane
+            h.shape = abi.RT_SHAPE_INFINITE_PLANE
+            h.p[:] = p.Point
+            h.n[:] = p.Normal
+            st = p.Style
+            if isinstance(st, InfinitePlaneStyle.LightSource):
+                h.style = abi.RT_STYLE_LIGHT_SOURCE
+                _set_texture(h, st.texture, table)
+            elif isinstance(st, InfinitePlaneStyle.PureReflection):
+                h.style = abi.RT_STYLE_PURE_REFLECTION
+                h.albedo = st.albedo
+                h.colour[:] = st.colour.as_tuple()
+            elif isinstance(st, InfinitePlaneStyle.LambertReflection):
+                h.style = abi.RT_STYLE_LAMBERT_REFLECTION
+                h.albedo = st.albedo
+                h.colour[:] = st.colour.as_tuple()
+            elif isinstance(st, InfinitePlaneStyle.FuzzedReflection):
+                h.style = abi.RT_STYLE_FUZZED_REFLECTION
+                h.albedo, h.fuzz = st.albedo, st.fuzz
+                h.colour[:] = st.colour.as_tuple()
+            else:
+                raise TypeError(f"unknown InfinitePlaneStyle {st!r}")
+        else:
+            raise TypeError(f"not a Hittable: {obj!r}")
+        out.append(h)
+    return out, table.entries, table.keep

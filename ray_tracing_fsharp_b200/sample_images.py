@@ -1,0 +1,221 @@
+"""Scene specifications for the five BASELINE.json configs, built with the mirrored
+F# surface in domain.py.  They follow RayTracing.App/SampleImages.fs where a sample exists
+(randomSpheres :812-960, earth :962-1010, glassSphere :506-597, movedCamera :710-810) but draw their
+random parameters from a fixed-seed numpy generator instead of `System.Random ()`, so the oracle
+and the GPU are fed identical scenes.  No file under /root/reference is read.
+
+Each function returns a `SceneSpec`: objects, camera arguments (for Camera.makeBasic), the two
+half-extents handed to Scene.render (F6: image is (2*max_w+1) x (2*max_h+1)), spp and depth.
+"""
+from dataclasses import dataclass
+from typing import Any, List, Tuple
+
+import numpy as np
+
+from .domain import (Colour, Hittable, InfinitePlane, InfinitePlaneStyle, ParameterisedTexture, Pixel, Sphere,
+                     SphereStyle, Texture)
+
+
+@dataclass
+class SceneSpec:
+    name: str
+    objects: List[Any]
+    spp: int
+    focal_length: float
+    aspect_ratio: float
+    origin: Tuple[float, float, float]
+    look_at: Tuple[float, float, float]
+    view_up: Tuple[float, float, float]
+    max_width_coord: int
+    max_height_coord: int
+    bounce_depth: int
+
+    @property
+    def view_direction(self):
+        v = np.asarray(self.look_at, float) - np.asarray(self.origin, float)
+        return tuple(v / np.sqrt(v @ v))
+
+    @property
+    def rows(self):
+        return 2 * self.max_height_coord + 1
+
+    @property
+    def cols(self):
+        return 2 * self.max_width_coord + 1
+
+
+def few_spheres(max_w=200, max_h=112, spp=16, depth=50) -> SceneSpec:
+    """C1: few-sphere Lambertian scene on a ground plane, 401x225, 16 spp, depth 50."""
+    objs = [
+        Hittable.InfinitePlane(InfinitePlane.make(
+            InfinitePlaneStyle.LambertReflection(0.5, Pixel(204, 204, 0)), (0.0, -0.5, 0.0), (0.0, 1.0, 0.0))),
+        Hittable.Sphere(Sphere.make(SphereStyle.LambertReflection(1.0, Texture.Colour(Pixel(100, 150, 200))),
+                                    (1.0, 0.0, 1.0), 0.5)),
+        Hittable.Sphere(Sphere.make(SphereStyle.LambertReflection(1.0, Texture.Colour(Pixel(25, 50, 120))),
+                                    (0.0, 0.0, 1.0), 0.5)),
+        Hittable.Sphere(Sphere.make(SphereStyle.LambertReflection(0.9, Texture.Colour(Colour.White)),
+                                    (-1.0, 0.0, 1.0), 0.5)),
+        Hittable.UnboundedSphere(Sphere.make(SphereStyle.LightSource(Texture.Colour(Pixel(200, 200, 200))),
+                                             (0.0, 0.0, 0.0), 200.0)),
+    ]
+    return SceneSpec("C1 few-sphere Lambertian on ground plane", objs, spp, 1.0, 16.0 / 9.0, (0.0, 0.0, 0.0),
+                     (0.0, 0.0, 1.0), (0.0, 1.0, 0.0), max_w, max_h, depth)
+
+
+def random_spheres(max_w=600, max_h=400, spp=500, depth=50, seed=1) -> SceneSpec:
+    """C2: the RTOW final scene exactly as randomSpheres (SampleImages.fs:812-960)."""
+    rng = np.random.default_rng(seed)
+    objs = []
+    for a in range(-11, 11):
+        for b in range(-11, 11):
+            material_choice = rng.random()
+            centre = (a + 0.9 * rng.random(), 0.2, b + 0.9 * rng.random())
+            d = np.asarray(centre) - np.asarray((4.0, 0.2, 0.0))
+            if d @ d > 0.9 * 0.9:
+                if material_choice < 0.8 - 1e-8:  # Float.compare materialChoice 0.8 = Less
+                    albedo = rng.random() * rng.random()
+                    style = SphereStyle.LambertReflection(albedo, Texture.Colour(Colour.random(rng)))
+                elif material_choice < 0.95 - 1e-8:
+                    albedo = rng.random() / 2.0 + 0.5
+                    fuzz = rng.random() / 2.0
+                    style = SphereStyle.FuzzedReflection(albedo, Texture.Colour(Colour.random(rng)), fuzz)
+                else:
+                    style = SphereStyle.Glass(1.0, Texture.Colour(Colour.White), 1.5)
+                objs.append(Hittable.Sphere(Sphere.make(style, centre, 0.2)))
+    objs.append(Hittable.Sphere(Sphere.make(SphereStyle.Glass(1.0, Texture.Colour(Colour.White), 1.5),
+                                            (0.0, 1.0, 0.0), 1.0)))
+    objs.append(Hittable.Sphere(Sphere.make(SphereStyle.LambertReflection(1.0, Texture.Colour(Pixel(80, 40, 20))),
+                                            (-4.0, 1.0, 0.0), 1.0)))
+    objs.append(Hittable.Sphere(Sphere.make(SphereStyle.PureReflection(1.0, Texture.Colour(Pixel(180, 150, 128))),
+                                            (4.0, 1.0, 0.0), 1.0)))
+    # Ceiling
+    objs.append(Hittable.UnboundedSphere(Sphere.make(SphereStyle.LightSource(Texture.Colour(Pixel(200, 200, 255))),
+                                                     (0.0, 0.0, 0.0), 2000.0)))
+    # Floor
+    objs.append(Hittable.UnboundedSphere(Sphere.make(SphereStyle.LambertReflection(0.5, Texture.Colour(Colour.White)),
+                                                     (0.0, -1000.0, 0.0), 1000.0)))
+    return SceneSpec("C2 RTOW final scene (random-spheres)", objs, spp, 10.0, 3.0 / 2.0, (13.0, 2.0, -3.0),
+                     (0.0, 0.0, 0.0), (0.0, 1.0, 0.0), max_w, max_h, depth)
+
+
+def synthetic_earthmap(width=1024, height=512, seed=7) -> np.ndarray:
+    """A 1024x512 RGB8 lat-long picture standing in for earthmap.jpg (same size and kind of content:
+    blue oceans, green/brown land, white caps).  The real JPEG is a reference asset and needs Skia's
+    decoder (parity unpinned at that boundary), so benchmarks use this deterministic
+    stand-in; row 0 is the top of the picture, as SKBitmap presents it."""
+    rng = np.random.default_rng(seed)
+    lat = np.linspace(np.pi / 2, -np.pi / 2, height)[:, None]
+    lon = np.linspace(-np.pi, np.pi, width, endpoint=False)[None, :]
+    x, y, z = np.cos(lat) * np.cos(lon), np.sin(lat) + 0 * lon, np.cos(lat) * np.sin(lon)
+    h = np.zeros((height, width))
+    for k in range(1, 7):
+        for _ in range(4):
+            w = rng.normal(size=3) * (2.0 ** k) * 0.6
+            ph = rng.uniform(0, 2 * np.pi)
+            h += np.sin(w[0] * x + w[1] * y + w[2] * z + ph) / (1.7 ** k)
+    h = (h - h.min()) / (h.max() - h.min())
+    land = h > 0.55
+    img = np.zeros((height, width, 3))
+    img[..., 0] = np.where(land, 60 + 150 * (h - 0.55) / 0.45, 10 + 30 * h)
+    img[..., 1] = np.where(land, 120 + 60 * (1 - h), 40 + 80 * h)
+    img[..., 2] = np.where(land, 40 + 40 * h, 120 + 120 * h)
+    cap = np.abs(lat) > 1.25
+    img[np.broadcast_to(cap, h.shape)] = 235
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+def earth(max_w=960, max_h=540, spp=256, depth=50, bitmap=None) -> SceneSpec:
+    """C3: `earth` (SampleImages.fs:962-1010) plus the two InfinitePlanes the config asks for."""
+    if bitmap is None:
+        bitmap = synthetic_earthmap()
+    texture = ParameterisedTexture.of_image(bitmap)
+    interpret = Sphere.plane_map_inverse(1.0, (0.0, 0.0, 0.0))
+    inv_sqrt2 = 1.0 / np.sqrt(2.0)
+    objs = [
+        Hittable.Sphere(Sphere.make(
+            SphereStyle.LambertReflection(1.0, ParameterisedTexture.to_texture(interpret, texture)),
+            (0.0, 0.0, 0.0), 1.0)),
+        Hittable.UnboundedSphere(Sphere.make(SphereStyle.LightSource(Texture.Colour(Pixel(130, 130, 200))),
+                                             (0.0, 0.0, 0.0), 200.0)),
+        Hittable.InfinitePlane(InfinitePlane.make(InfinitePlaneStyle.LambertReflection(0.6, Pixel(200, 200, 180)),
+                                                  (0.0, -1.0, 0.0), (0.0, 1.0, 0.0))),
+        Hittable.InfinitePlane(InfinitePlane.make(InfinitePlaneStyle.PureReflection(0.9, Pixel(230, 230, 240)),
+                                                  (-3.0, 0.0, 3.0), (inv_sqrt2, 0.0, -inv_sqrt2))),
+    ]
+    return SceneSpec("C3 earthmap image-textured sphere + planes", objs, spp, 12.0, 16.0 / 9.0, (13.0, 2.0, -3.0),
+                     (0.0, 0.0, 0.0), (0.0, 1.0, 0.0), max_w, max_h, depth)
+
+
+def mixed_planes(max_w=960, max_h=540, spp=1024, depth=100) -> SceneSpec:
+    """C4: all four InfinitePlane styles + Glass / Dielectric / hollow-shell spheres (F13: the
+    reference has no finite Plane primitive and no dielectric plane; refraction comes from spheres)."""
+    s3 = 1.0 / np.sqrt(3.0)
+    objs = [
+        # Lambert floor
+        Hittable.InfinitePlane(InfinitePlane.make(InfinitePlaneStyle.LambertReflection(0.5, Pixel(204, 204, 0)),
+                                                  (0.0, -0.5, 0.0), (0.0, 1.0, 0.0))),
+        # mirror wall on the right
+        Hittable.InfinitePlane(InfinitePlane.make(InfinitePlaneStyle.PureReflection(0.9, Pixel(220, 220, 255)),
+                                                  (3.0, 0.0, 0.0), (-1.0, 0.0, 0.0))),
+        # fuzzed wall at the back
+        Hittable.InfinitePlane(InfinitePlane.make(InfinitePlaneStyle.FuzzedReflection(0.8, Pixel(255, 200, 200), 0.3),
+                                                  (0.0, 0.0, 6.0), (0.0, 0.0, -1.0))),
+        # emitting ceiling
+        Hittable.InfinitePlane(InfinitePlane.make(InfinitePlaneStyle.LightSource(Texture.Colour(Pixel(255, 255, 255))),
+                                                  (0.0, 4.0, 0.0), (0.0, -1.0, 0.0))),
+        Hittable.Sphere(Sphere.make(SphereStyle.Glass(0.9, Texture.Colour(Colour.White), 1.5), (-1.1, 0.0, 2.0), 0.5)),
+        Hittable.Sphere(Sphere.make(SphereStyle.Dielectric(0.95, Texture.Colour(Pixel(200, 255, 200)), 1.5, 0.9),
+                                    (0.0, 0.0, 2.5), 0.5)),
+        # hollow shell: outer bounded, inner UnboundedSphere with negative radius so that it IS intersected (F16)
+        Hittable.Sphere(Sphere.make(SphereStyle.Glass(1.0, Texture.Colour(Colour.White), 1.5), (1.1, 0.0, 2.0), 0.5)),
+        Hittable.UnboundedSphere(Sphere.make(SphereStyle.Glass(1.0, Texture.Colour(Colour.White), 1.0 / 1.5),
+                                             (1.1, 0.0, 2.0), -0.45)),
+        # a bounded negative-radius sphere: never hit in the reference (F16) — pins that quirk
+        Hittable.Sphere(Sphere.make(SphereStyle.LambertReflection(1.0, Texture.Colour(Colour.Red)), (0.0, 1.2, 3.0), -0.4)),
+        Hittable.Sphere(Sphere.make(SphereStyle.LambertReflection(0.8, Texture.Colour(Pixel(25, 50, 120))),
+                                    (-2.0, 0.1, 3.5), 0.6)),
+        Hittable.Sphere(Sphere.make(SphereStyle.FuzzedReflection(0.9, Texture.Colour(Pixel(255, 215, 0)), 0.1),
+                                    (2.0, 0.1, 4.0), 0.6)),
+        # light leaking in from behind the camera as well, so the scene is enclosed
+        Hittable.UnboundedSphere(Sphere.make(SphereStyle.LightSource(Texture.Colour(Pixel(130, 130, 200))),
+                                             (0.0, 0.0, 0.0), 200.0)),
+    ]
+    return SceneSpec("C4 InfinitePlane mixed-primitive scene with dielectric refraction", objs, spp, 1.0, 16.0 / 9.0,
+                     (0.0, 0.6, -1.5), (0.0, 0.2, 2.0), (0.0, 1.0, 0.0), max_w, max_h, depth)
+
+
+def many_spheres(n=100_000, max_w=1920, max_h=1080, spp=4096, depth=50, seed=5) -> SceneSpec:
+    """C5: synthetic 100k random spheres, materials 80/15/5 % Lambert/Fuzzed/Glass as in C2."""
+    rng = np.random.default_rng(seed)
+    cx = rng.uniform(-50, 50, n)
+    cy = rng.uniform(0.2, 10, n)
+    cz = rng.uniform(-50, 50, n)
+    rad = rng.uniform(0.05, 0.3, n)
+    choice = rng.random(n)
+    u1, u2 = rng.random(n), rng.random(n)
+    cols = rng.integers(0, 256, size=(n, 3))
+    objs = []
+    for i in range(n):
+        col = Texture.Colour(Pixel(int(cols[i, 0]), int(cols[i, 1]), int(cols[i, 2])))
+        if choice[i] < 0.8:
+            style = SphereStyle.LambertReflection(float(u1[i] * u2[i]), col)
+        elif choice[i] < 0.95:
+            style = SphereStyle.FuzzedReflection(float(u1[i] / 2 + 0.5), col, float(u2[i] / 2))
+        else:
+            style = SphereStyle.Glass(1.0, Texture.Colour(Colour.White), 1.5)
+        objs.append(Hittable.Sphere(Sphere.make(style, (float(cx[i]), float(cy[i]), float(cz[i])), float(rad[i]))))
+    objs.append(Hittable.UnboundedSphere(Sphere.make(SphereStyle.LightSource(Texture.Colour(Pixel(200, 200, 255))),
+                                                     (0.0, 0.0, 0.0), 2000.0)))
+    objs.append(Hittable.UnboundedSphere(Sphere.make(SphereStyle.LambertReflection(0.5, Texture.Colour(Colour.White)),
+                                                     (0.0, -1000.0, 0.0), 1000.0)))
+    return SceneSpec(f"C5 synthetic {n} random spheres", objs, spp, 4.0, 16.0 / 9.0, (60.0, 20.0, -60.0),
+                     (0.0, 0.0, 0.0), (0.0, 1.0, 0.0), max_w, max_h, depth)
+
+
+CONFIGS = {
+    "C1": few_spheres,
+    "C2": random_spheres,
+    "C3": earth,
+    "C4": mixed_planes,
+    "C5": many_spheres,
+}
