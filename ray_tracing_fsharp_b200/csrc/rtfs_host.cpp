@@ -1,0 +1,622 @@
+// rtfs_host.cpp — host half of librtfs_b200.so: error plumbing, Camera.makeBasic, the P3 writer,
+// the two BVH builders and the scene handle.  Nothing in this file needs a GPU.
+#include "rtfs_internal.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <numeric>
+
+namespace rtfs {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string &msg) { g_last_error = msg; }
+int fail(int code, const std::string &msg) {
+    g_last_error = msg;
+    return code;
+}
+
+namespace {
+
+struct D3 {
+    double x, y, z;
+};
+inline D3 operator+(D3 a, D3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline D3 operator-(D3 a, D3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline D3 operator*(double s, D3 a) { return {s * a.x, s * a.y, s * a.z}; }
+inline double dot(D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline D3 cross(D3 a, D3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - b.x * a.y}; }
+inline D3 load(const double *p) { return {p[0], p[1], p[2]}; }
+inline void store(double *p, D3 v) {
+    p[0] = v.x;
+    p[1] = v.y;
+    p[2] = v.z;
+}
+constexpr double kTol = 1e-8; // Float.tolerance, RayTracing/Float.fs:80
+// Vector.unitise (Point.fs:28-35): fails when |v.v| < 1e-8, multiplies by the reciprocal root.
+inline bool unitise(D3 v, D3 &out) {
+    double d = dot(v, v);
+    if (std::fabs(d) < kTol) return false;
+    out = (1.0 / std::sqrt(d)) * v;
+    return true;
+}
+
+inline float round_down(double v) {
+    float f = float(v);
+    if (double(f) > v) f = std::nextafterf(f, -std::numeric_limits<float>::infinity());
+    return f;
+}
+inline float round_up(double v) {
+    float f = float(v);
+    if (double(f) < v) f = std::nextafterf(f, std::numeric_limits<float>::infinity());
+    return f;
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------------
+// BoundingBoxTree.make, RayTracing/BoundingBoxTree.fs:9-43
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct RefBox {
+    double mn[3], mx[3];
+};
+inline RefBox sphere_box(const RtHittable &h) { // Sphere.make, Sphere.fs:333-336 (inverted when radius < 0)
+    RefBox b;
+    for (int a = 0; a < 3; ++a) {
+        b.mn[a] = h.p[a] + (-h.radius);
+        b.mx[a] = h.p[a] + h.radius;
+    }
+    return b;
+}
+inline RefBox merge(const RefBox &i, const RefBox &j) { // BoundingBox.mergeTwo, BoundingBox.fs:96-108
+    RefBox o;
+    for (int a = 0; a < 3; ++a) {
+        o.mn[a] = std::min(i.mn[a], j.mn[a]);
+        o.mx[a] = std::max(i.mx[a], j.mx[a]);
+    }
+    return o;
+}
+inline double volume(const RefBox &b) { return (b.mx[0] - b.mn[0]) * (b.mx[1] - b.mn[1]) * (b.mx[2] - b.mn[2]); }
+inline RefBox merge_all(const RtHittable *objs, const std::vector<int32_t> &v) {
+    RefBox b = sphere_box(objs[v[0]]);
+    for (size_t i = 1; i < v.size(); ++i) b = merge(b, sphere_box(objs[v[i]]));
+    return b;
+}
+
+int32_t ref_go(const RtHittable *objs, const std::vector<int32_t> &boxes, std::vector<HostNode> &out) {
+    int32_t me = int32_t(out.size());
+    out.push_back(HostNode{});
+    RefBox all = merge_all(objs, boxes);
+    auto put_box = [&](const RefBox &b) {
+        for (int a = 0; a < 3; ++a) {
+            out[me].mn[a] = b.mn[a];
+            out[me].mx[a] = b.mx[a];
+        }
+    };
+    put_box(all);
+    out[me].right = -1;
+    out[me].prim = -1;
+    if (boxes.size() == 1) {
+        out[me].prim = boxes[0];
+        return me;
+    }
+    if (boxes.size() == 2) {
+        ref_go(objs, {boxes[0]}, out);
+        int32_t r = ref_go(objs, {boxes[1]}, out);
+        out[me].right = r;
+        return me;
+    }
+    std::vector<int32_t> best_left, best_right;
+    double best_cost = 0.0;
+    for (int axis = 0; axis < 3; ++axis) {
+        std::vector<int32_t> sorted = boxes;
+        // Array.sortBy is unstable in .NET; a stable sort is one of its admissible outcomes.
+        std::stable_sort(sorted.begin(), sorted.end(), [&](int32_t a, int32_t b) {
+            return (objs[a].p[axis] + (-objs[a].radius)) < (objs[b].p[axis] + (-objs[b].radius));
+        });
+        size_t half = sorted.size() / 2;
+        std::vector<int32_t> left(sorted.begin(), sorted.begin() + half + 1); // boxes.[0 .. n/2] is inclusive
+        std::vector<int32_t> right(sorted.begin() + half + 1, sorted.end());
+        double cost = volume(merge_all(objs, left)) + volume(merge_all(objs, right));
+        if (axis == 0 || cost < best_cost) { // Array.minBy keeps the first minimum
+            best_cost = cost;
+            best_left.swap(left);
+            best_right.swap(right);
+        }
+    }
+    ref_go(objs, best_left, out);
+    int32_t r = ref_go(objs, best_right, out);
+    out[me].right = r;
+    return me;
+}
+} // namespace
+
+void build_reference_tree(const RtHittable *objs, const std::vector<int32_t> &prims, std::vector<HostNode> &out) {
+    out.clear();
+    if (prims.empty()) return;
+    ref_go(objs, prims, out);
+}
+
+// ---------------------------------------------------------------------------------------------
+// SAH BVH2 for the render kernels
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct BuildPrim {
+    float mn[3], mx[3];
+    float c[3];
+    int32_t obj;
+};
+struct FBox {
+    float mn[3], mx[3];
+    void reset() {
+        for (int a = 0; a < 3; ++a) {
+            mn[a] = std::numeric_limits<float>::infinity();
+            mx[a] = -std::numeric_limits<float>::infinity();
+        }
+    }
+    void grow(const float *pmn, const float *pmx) {
+        for (int a = 0; a < 3; ++a) {
+            mn[a] = std::min(mn[a], pmn[a]);
+            mx[a] = std::max(mx[a], pmx[a]);
+        }
+    }
+    double area() const {
+        double dx = double(mx[0]) - mn[0], dy = double(mx[1]) - mn[1], dz = double(mx[2]) - mn[2];
+        if (dx < 0 || dy < 0 || dz < 0) return 0.0;
+        return 2.0 * (dx * dy + dy * dz + dz * dx);
+    }
+};
+
+struct SahBuilder {
+    std::vector<BuildPrim> prims;
+    const RtHittable *objs;
+    HostSceneLayout *layout;
+    int max_depth = 0;
+
+    FBox bounds(int lo, int hi) const {
+        FBox b;
+        b.reset();
+        for (int i = lo; i < hi; ++i) b.grow(prims[i].mn, prims[i].mx);
+        return b;
+    }
+    int32_t emit_leaf(int i) {
+        const RtHittable &h = objs[prims[i].obj];
+        int32_t idx = int32_t(layout->spheres.size());
+        layout->spheres.push_back(DSphere{float(h.p[0]), float(h.p[1]), float(h.p[2]), float(h.radius)});
+        leaf_obj.push_back(prims[i].obj);
+        return ~idx;
+    }
+    std::vector<int32_t> leaf_obj;
+
+    int split(int lo, int hi, int depth) {
+        int n = hi - lo;
+        int mid = -1;
+        if (n > 2 && depth < 40) {
+            FBox cb;
+            cb.reset();
+            for (int i = lo; i < hi; ++i) cb.grow(prims[i].c, prims[i].c);
+            constexpr int BINS = 16;
+            double best = std::numeric_limits<double>::infinity();
+            int best_axis = -1, best_bin = -1;
+            for (int axis = 0; axis < 3; ++axis) {
+                float ext = cb.mx[axis] - cb.mn[axis];
+                if (!(ext > 0.f)) continue;
+                FBox bb[BINS];
+                int cnt[BINS] = {0};
+                for (auto &b : bb) b.reset();
+                float scale = float(BINS) / ext;
+                for (int i = lo; i < hi; ++i) {
+                    int k = std::min(BINS - 1, std::max(0, int((prims[i].c[axis] - cb.mn[axis]) * scale)));
+                    bb[k].grow(prims[i].mn, prims[i].mx);
+                    cnt[k]++;
+                }
+                double right_area[BINS];
+                int right_cnt[BINS];
+                FBox acc;
+                acc.reset();
+                int c = 0;
+                for (int k = BINS - 1; k > 0; --k) {
+                    if (cnt[k]) acc.grow(bb[k].mn, bb[k].mx);
+                    c += cnt[k];
+                    right_area[k] = acc.area();
+                    right_cnt[k] = c;
+                }
+                acc.reset();
+                c = 0;
+                for (int k = 0; k < BINS - 1; ++k) {
+                    if (cnt[k]) acc.grow(bb[k].mn, bb[k].mx);
+                    c += cnt[k];
+                    if (c == 0 || right_cnt[k + 1] == 0) continue;
+                    double cost = acc.area() * c + right_area[k + 1] * right_cnt[k + 1];
+                    if (cost < best) {
+                        best = cost;
+                        best_axis = axis;
+                        best_bin = k;
+                    }
+                }
+            }
+            if (best_axis >= 0) {
+                float ext = cb.mx[best_axis] - cb.mn[best_axis];
+                float scale = float(BINS) / ext;
+                auto it = std::partition(prims.begin() + lo, prims.begin() + hi, [&](const BuildPrim &p) {
+                    int k = std::min(BINS - 1, std::max(0, int((p.c[best_axis] - cb.mn[best_axis]) * scale)));
+                    return k <= best_bin;
+                });
+                mid = int(it - prims.begin());
+            }
+        }
+        if (mid <= lo || mid >= hi) { // median split on the widest centroid axis
+            FBox cb;
+            cb.reset();
+            for (int i = lo; i < hi; ++i) cb.grow(prims[i].c, prims[i].c);
+            int axis = 0;
+            for (int a = 1; a < 3; ++a)
+                if (cb.mx[a] - cb.mn[a] > cb.mx[axis] - cb.mn[axis]) axis = a;
+            mid = lo + n / 2;
+            std::nth_element(prims.begin() + lo, prims.begin() + mid, prims.begin() + hi,
+                             [&](const BuildPrim &a, const BuildPrim &b) { return a.c[axis] < b.c[axis]; });
+        }
+        return mid;
+    }
+
+    // builds an internal node over [lo, hi), hi - lo >= 2; returns its index
+    int32_t build(int lo, int hi, int depth) {
+        max_depth = std::max(max_depth, depth);
+        int32_t me = int32_t(layout->nodes.size());
+        layout->nodes.push_back(DNode{});
+        int mid = split(lo, hi, depth);
+        FBox lb = bounds(lo, mid), rb = bounds(mid, hi);
+        int32_t left = (mid - lo == 1) ? emit_leaf(lo) : build(lo, mid, depth + 1);
+        int32_t right = (hi - mid == 1) ? emit_leaf(mid) : build(mid, hi, depth + 1);
+        DNode &nd = layout->nodes[me];
+        for (int a = 0; a < 3; ++a) {
+            nd.l_mn[a] = lb.mn[a];
+            nd.l_mx[a] = lb.mx[a];
+            nd.r_mn[a] = rb.mn[a];
+            nd.r_mx[a] = rb.mx[a];
+        }
+        nd.left = left;
+        nd.right = right;
+        nd.pad0 = nd.pad1 = 0;
+        return me;
+    }
+};
+
+DMaterial make_material(const RtHittable &h, int32_t host_index) {
+    DMaterial m{};
+    m.albedo = h.albedo;
+    m.p0 = 0.f;
+    m.p1 = 0.f;
+    switch (h.style) {
+    case RT_STYLE_FUZZED_REFLECTION: m.p0 = float(h.fuzz); break;
+    case RT_STYLE_DIELECTRIC:
+        m.p0 = float(h.ior);
+        m.p1 = float(h.prob);
+        break;
+    case RT_STYLE_GLASS: m.p0 = float(h.ior); break;
+    case RT_STYLE_LIGHT_SOURCE_CAP: m.p0 = float(h.p[0] + (h.radius - (h.radius / 4.0))); break; // Sphere.fs:191-192
+    default: break;
+    }
+    m.style_rgb = (uint32_t(h.style) << 24) | (uint32_t(h.colour[0]) << 16) | (uint32_t(h.colour[1]) << 8) | uint32_t(h.colour[2]);
+    m.texture = h.texture;
+    m.flags = 0;
+    if (h.shape != RT_SHAPE_INFINITE_PLANE && std::fabs(h.radius - 0.0) >= kTol && h.radius < 0.0) m.flags |= 1u; // Float.compare r 0 = Less
+    if (h.shape == RT_SHAPE_INFINITE_PLANE) m.flags |= 2u;
+    m.host_index = host_index;
+    return m;
+}
+
+void export_sah(const HostSceneLayout &L, const std::vector<int32_t> &leaf_obj, int32_t ref, const float *mn, const float *mx,
+                std::vector<HostNode> &out) {
+    int32_t me = int32_t(out.size());
+    out.push_back(HostNode{});
+    for (int a = 0; a < 3; ++a) {
+        out[me].mn[a] = mn[a];
+        out[me].mx[a] = mx[a];
+    }
+    out[me].right = -1;
+    out[me].prim = -1;
+    if (ref < 0) {
+        out[me].prim = leaf_obj[~ref];
+        return;
+    }
+    const DNode nd = L.nodes[ref];
+    export_sah(L, leaf_obj, nd.left, nd.l_mn, nd.l_mx, out);
+    int32_t r = int32_t(out.size());
+    export_sah(L, leaf_obj, nd.right, nd.r_mn, nd.r_mx, out);
+    out[me].right = r;
+}
+} // namespace
+
+void build_device_layout(const RtHittable *objs, int32_t n_objs, const std::vector<HostNode> &ref_tree,
+                         HostSceneLayout &L, std::vector<HostNode> &sah_tree_out) {
+    L = HostSceneLayout{};
+    sah_tree_out.clear();
+    SahBuilder b;
+    b.objs = objs;
+    b.layout = &L;
+    std::vector<int32_t> unbounded;
+    for (int32_t i = 0; i < n_objs; ++i) {
+        const RtHittable &h = objs[i];
+        if (h.shape != RT_SHAPE_SPHERE) {
+            unbounded.push_back(i);
+            continue;
+        }
+        if (h.radius < 0.0) continue; // inverted box: never hit in the reference (F16); kept only in the reference tree
+        BuildPrim p;
+        float cf[3] = {float(h.p[0]), float(h.p[1]), float(h.p[2])};
+        float rf = float(h.radius);
+        for (int a = 0; a < 3; ++a) {
+            p.mn[a] = round_down(double(cf[a]) - double(rf));
+            p.mx[a] = round_up(double(cf[a]) + double(rf));
+            p.c[a] = cf[a];
+        }
+        p.obj = i;
+        b.prims.push_back(p);
+    }
+    int n = int(b.prims.size());
+    if (n == 1) {
+        // a single leaf: wrap it in a node whose right child is an empty (never hit) box
+        L.nodes.push_back(DNode{});
+        int32_t leaf = b.emit_leaf(0);
+        DNode &nd = L.nodes[0];
+        for (int a = 0; a < 3; ++a) {
+            nd.l_mn[a] = b.prims[0].mn[a];
+            nd.l_mx[a] = b.prims[0].mx[a];
+            nd.r_mn[a] = std::numeric_limits<float>::infinity();
+            nd.r_mx[a] = -std::numeric_limits<float>::infinity();
+        }
+        nd.left = leaf;
+        nd.right = leaf;
+        L.root_is_leaf = 1;
+        b.max_depth = 1;
+    } else if (n >= 2) {
+        b.build(0, n, 1);
+    }
+    L.n_bounded = int32_t(L.spheres.size());
+    L.max_depth = b.max_depth;
+    std::vector<int32_t> device_id_of(n_objs, -1);
+    for (int32_t k = 0; k < L.n_bounded; ++k) {
+        L.materials.push_back(make_material(objs[b.leaf_obj[k]], b.leaf_obj[k]));
+        device_id_of[b.leaf_obj[k]] = k;
+    }
+    for (int32_t i : unbounded) {
+        const RtHittable &h = objs[i];
+        DUnbounded u{};
+        for (int a = 0; a < 3; ++a) {
+            u.p[a] = h.p[a];
+            u.n[a] = float(h.n[a]);
+        }
+        u.r2 = h.radius * h.radius; // Sphere.make, Sphere.fs:326
+        u.r = float(h.radius);
+        u.shape = h.shape;
+        device_id_of[i] = L.n_bounded + int32_t(L.unbounded.size());
+        L.unbounded.push_back(u);
+        L.materials.push_back(make_material(h, i));
+    }
+    L.device_id_of = device_id_of; // bounded spheres with negative radius keep id -1: they can never be returned
+    for (const HostNode &hn : ref_tree) {
+        DRefNode r{};
+        for (int a = 0; a < 3; ++a) {
+            bool inverted = hn.mn[a] > hn.mx[a];
+            r.mn[a] = inverted ? float(hn.mn[a]) : round_down(hn.mn[a]);
+            r.mx[a] = inverted ? float(hn.mx[a]) : round_up(hn.mx[a]);
+        }
+        r.right = hn.right;
+        r.prim = hn.prim >= 0 ? device_id_of[hn.prim] : -1;
+        L.ref_nodes.push_back(r);
+    }
+    if (n >= 1) {
+        FBox rootb = b.bounds(0, n);
+        if (n == 1) {
+            export_sah(L, b.leaf_obj, L.nodes[0].left, rootb.mn, rootb.mx, sah_tree_out);
+        } else {
+            export_sah(L, b.leaf_obj, 0, rootb.mn, rootb.mx, sah_tree_out);
+        }
+    }
+}
+
+} // namespace rtfs
+
+using namespace rtfs;
+
+// =================================================================================================
+// C ABI — host-side entry points
+// =================================================================================================
+extern "C" {
+
+int rt_abi_version(void) { return RT_ABI_VERSION; }
+const char *rt_last_error(void) { return g_last_error.c_str(); }
+
+// Camera.makeBasic, RayTracing/Camera.fs:34-59
+int rt_camera_make_basic(int32_t samples_per_pixel, double focal_length, double aspect_ratio, const double origin[3],
+                         const double view_direction[3], const double view_up[3], RtCamera *out) {
+    if (!origin || !view_direction || !view_up || !out) return fail(RT_ERR_INVALID_ARGUMENT, "rt_camera_make_basic: null argument");
+    D3 o = load(origin), view = load(view_direction), up = load(view_up);
+    if (std::fabs(dot(view, view) - 1.0) > 1e-6)
+        return fail(RT_ERR_INVALID_ARGUMENT, "rt_camera_make_basic: view_direction must be a unit vector (UnitVector in the reference)");
+    const double height = 2.0;
+    D3 corner = o + focal_length * view; // Ray.walkAlong view focalLength
+    // Plane.makeNormalTo' corner viewDirection, Plane.fs:22-38
+    D3 v1 = (std::fabs(view.z - 0.0) < kTol) ? D3{0.0, 0.0, 1.0} : D3{1.0, 1.0, (-view.x - view.y) / view.z};
+    D3 p_v2, p_v1;
+    if (!unitise(cross(view, v1), p_v2) || !unitise(v1, p_v1))
+        return fail(RT_ERR_DEGENERATE, "rt_camera_make_basic: Plane.makeNormalTo failed to normalise (the reference throws)");
+    // Plane.basis viewUp viewPlane, Plane.fs:82-97
+    D3 upn;
+    if (!unitise(up, upn)) return fail(RT_ERR_DEGENERATE, "rt_camera_make_basic: viewUp has zero length (the reference throws)");
+    double c1 = dot(p_v1, upn), c2 = dot(p_v2, upn);
+    D3 yv, xv;
+    if (!unitise(c1 * p_v1 + c2 * p_v2, yv) || !unitise(c2 * p_v1 + (-c1) * p_v2, xv))
+        return fail(RT_ERR_DEGENERATE, "rt_camera_make_basic: viewUp is parallel to the view direction (the reference throws)");
+    std::memset(out, 0, sizeof *out);
+    store(out->view_origin, o);
+    store(out->view_dir, view);
+    store(out->xaxis_origin, corner);
+    store(out->xaxis_dir, xv);
+    store(out->yaxis_dir, yv);
+    out->viewport_height = height;
+    out->viewport_width = aspect_ratio * height;
+    out->focal_length = focal_length;
+    out->samples_per_pixel = samples_per_pixel;
+    out->bounce_depth = 150; // Camera.fs:58
+    return RT_OK;
+}
+
+// PixelOutput.correct, RayTracing/ImageOutput.fs:11-18
+uint8_t rt_gamma_correct(uint8_t b) {
+    int i = int(std::nearbyint(std::sqrt(double(b) / 255.0) * 255.0)); // Math.Round: half to even
+    if (i == 256) i = 255;
+    return uint8_t(i);
+}
+
+// ImageOutput.writePpm, RayTracing/ImageOutput.fs:163-197
+static void ppm_build(const uint8_t *rgb, int32_t rows, int32_t cols, bool gamma, std::string &s) {
+    uint8_t lut[256];
+    for (int i = 0; i < 256; ++i) lut[i] = gamma ? rt_gamma_correct(uint8_t(i)) : uint8_t(i);
+    char num[256][4];
+    int len[256];
+    for (int i = 0; i < 256; ++i) len[i] = std::snprintf(num[i], 4, "%d", i);
+    s.clear();
+    s.reserve(size_t(rows) * cols * 12 + 32);
+    s += "P3\n";
+    s += std::to_string(cols) + " " + std::to_string(rows) + "\n";
+    s += "255\n";
+    for (int32_t r = 0; r < rows; ++r) {
+        for (int32_t c = 0; c < cols; ++c) {
+            const uint8_t *p = rgb + (size_t(r) * cols + c) * 3;
+            for (int k = 0; k < 3; ++k) {
+                uint8_t v = lut[p[k]];
+                s.append(num[v], size_t(len[v]));
+                if (k != 2) s.push_back(' ');
+            }
+            if (c != cols - 1) s.push_back(' ');
+        }
+        if (r != rows - 1) s.push_back('\n');
+    }
+}
+int rt_ppm_format(const uint8_t *rgb, int32_t rows, int32_t cols, int32_t gamma_correct, char *out, size_t cap, size_t *len) {
+    if (!rgb || rows <= 0 || cols <= 0 || !len) return fail(RT_ERR_INVALID_ARGUMENT, "rt_ppm_format: bad argument");
+    std::string s;
+    ppm_build(rgb, rows, cols, gamma_correct != 0, s);
+    *len = s.size();
+    if (out && cap) std::memcpy(out, s.data(), std::min(cap, s.size()));
+    return RT_OK;
+}
+int rt_ppm_write_file(const uint8_t *rgb, int32_t rows, int32_t cols, int32_t gamma_correct, const char *path) {
+    if (!rgb || rows <= 0 || cols <= 0 || !path) return fail(RT_ERR_INVALID_ARGUMENT, "rt_ppm_write_file: bad argument");
+    std::string s;
+    ppm_build(rgb, rows, cols, gamma_correct != 0, s);
+    FILE *f = std::fopen(path, "wb");
+    if (!f) return fail(RT_ERR_IO, std::string("rt_ppm_write_file: cannot open ") + path);
+    size_t w = std::fwrite(s.data(), 1, s.size(), f);
+    std::fclose(f);
+    if (w != s.size()) return fail(RT_ERR_IO, "rt_ppm_write_file: short write");
+    return RT_OK;
+}
+
+// Scene.make, RayTracing/Scene.fs:15-28
+int rt_scene_create(const RtHittable *objects, int32_t n_objects, const RtTexture *textures, int32_t n_textures,
+                    int32_t device, RtScene **out) {
+    if (!out) return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_create: out is null");
+    *out = nullptr;
+    if (n_objects < 0 || n_textures < 0 || (n_objects > 0 && !objects) || (n_textures > 0 && !textures))
+        return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_create: bad array arguments");
+    for (int32_t i = 0; i < n_objects; ++i) {
+        const RtHittable &h = objects[i];
+        if (h.shape < RT_SHAPE_SPHERE || h.shape > RT_SHAPE_INFINITE_PLANE)
+            return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_create: object " + std::to_string(i) + " has an unknown shape");
+        if (h.style < RT_STYLE_LIGHT_SOURCE || h.style > RT_STYLE_GLASS)
+            return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_create: object " + std::to_string(i) + " has an unknown style");
+        if (h.shape == RT_SHAPE_INFINITE_PLANE) {
+            // InfinitePlaneStyle has four cases only (InfinitePlane.fs:3-13, F13)
+            if (h.style == RT_STYLE_LIGHT_SOURCE_CAP || h.style == RT_STYLE_DIELECTRIC || h.style == RT_STYLE_GLASS)
+                return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_create: object " + std::to_string(i) + ": InfinitePlaneStyle has no such case");
+            double nn = h.n[0] * h.n[0] + h.n[1] * h.n[1] + h.n[2] * h.n[2];
+            if (std::fabs(nn - 1.0) > 1e-6)
+                return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_create: object " + std::to_string(i) + ": plane normal must be a unit vector");
+            if (h.style != RT_STYLE_LIGHT_SOURCE && h.texture >= 0)
+                return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_create: object " + std::to_string(i) + ": reflecting planes carry a colour, not a texture");
+        }
+        if (h.texture >= n_textures) return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_create: object " + std::to_string(i) + " references a missing texture");
+        for (int a = 0; a < 3; ++a)
+            if (!std::isfinite(h.p[a])) return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_create: object " + std::to_string(i) + " has a non-finite coordinate");
+        if (h.shape != RT_SHAPE_INFINITE_PLANE && !std::isfinite(h.radius))
+            return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_create: object " + std::to_string(i) + " has a non-finite radius");
+    }
+    for (int32_t t = 0; t < n_textures; ++t) {
+        const RtTexture &x = textures[t];
+        if (x.kind == RT_TEX_IMAGE) {
+            if (x.width <= 0 || x.height <= 0 || !x.rgb8) return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_create: image texture " + std::to_string(t) + " is empty");
+        } else if (x.kind == RT_TEX_CHECKERED) {
+            if (x.even < 0 || x.even >= n_textures || x.odd < 0 || x.odd >= n_textures || x.even == t || x.odd == t)
+                return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_create: checkered texture " + std::to_string(t) + " has bad sub-textures");
+        } else if (x.kind != RT_TEX_COLOUR) {
+            return fail(RT_ERR_UNSUPPORTED, "rt_scene_create: texture " + std::to_string(t) + " is of a kind the device cannot evaluate (closures must be baked to an image)");
+        }
+        if (x.kind != RT_TEX_COLOUR && !(std::fabs(x.map_radius) > 0.0))
+            return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_create: texture " + std::to_string(t) + " has map_radius 0");
+    }
+    auto *s = new RtScene();
+    s->objects.assign(objects, objects + n_objects);
+    s->textures.assign(textures, textures + n_textures);
+    s->texture_pixels.resize(n_textures);
+    for (int32_t t = 0; t < n_textures; ++t) {
+        if (textures[t].kind == RT_TEX_IMAGE) {
+            size_t bytes = size_t(textures[t].width) * textures[t].height * 3;
+            s->texture_pixels[t].assign(textures[t].rgb8, textures[t].rgb8 + bytes);
+            s->textures[t].rgb8 = s->texture_pixels[t].data();
+        } else {
+            s->textures[t].rgb8 = nullptr;
+        }
+    }
+    std::vector<int32_t> bounded;
+    for (int32_t i = 0; i < n_objects; ++i)
+        if (objects[i].shape == RT_SHAPE_SPHERE) bounded.push_back(i); // Hittable.BoundingBox, Hittable.fs:14-18
+    build_reference_tree(s->objects.data(), bounded, s->ref_tree);
+    build_device_layout(s->objects.data(), n_objects, s->ref_tree, s->layout, s->sah_tree);
+    if (s->layout.max_depth > 60) {
+        delete s;
+        return fail(RT_ERR_UNSUPPORTED, "rt_scene_create: BVH deeper than the traversal stack");
+    }
+    s->device = device;
+    if (device >= 0) {
+        int rc = device_scene_upload(s);
+        if (rc != RT_OK) {
+            delete s;
+            return rc;
+        }
+    }
+    *out = s;
+    return RT_OK;
+}
+
+void rt_scene_destroy(RtScene *scene) {
+    if (!scene) return;
+    if (scene->dev) device_scene_free(scene);
+    delete scene;
+}
+
+int rt_scene_bvh_node_count(const RtScene *scene, int32_t which) {
+    if (!scene) return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_bvh_node_count: null scene");
+    return int(which == RT_BVH_REFERENCE ? scene->ref_tree.size() : scene->sah_tree.size());
+}
+int rt_scene_bvh_nodes(const RtScene *scene, int32_t which, double *bounds, int32_t *right, int32_t *prim) {
+    if (!scene || !bounds || !right || !prim) return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_bvh_nodes: null argument");
+    const auto &t = which == RT_BVH_REFERENCE ? scene->ref_tree : scene->sah_tree;
+    for (size_t i = 0; i < t.size(); ++i) {
+        for (int a = 0; a < 3; ++a) {
+            bounds[6 * i + a] = t[i].mn[a];
+            bounds[6 * i + 3 + a] = t[i].mx[a];
+        }
+        right[i] = t[i].right;
+        prim[i] = t[i].prim;
+    }
+    return RT_OK;
+}
+size_t rt_scene_device_bytes(const RtScene *scene) { return scene ? device_scene_bytes(scene) : 0; }
+
+} // extern "C"

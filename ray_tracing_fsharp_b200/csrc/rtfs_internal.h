@@ -1,0 +1,129 @@
+// rtfs_internal.h — types shared by the host (rtfs_host.cpp) and device (rtfs_device.cu) halves of
+// librtfs_b200.so.  Not part of the public ABI.
+#pragma once
+#include "../../include/rtfs_b200.h"
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace rtfs {
+
+// ---- error plumbing ---------------------------------------------------------------------------
+void set_error(const std::string &msg);
+int fail(int code, const std::string &msg);
+
+// ---- host BVH ---------------------------------------------------------------------------------
+// Flattened tree in DFS pre-order (left child = i + 1), the format rt_scene_bvh_nodes exposes.
+struct HostNode {
+    double mn[3], mx[3];
+    int32_t right; // -1: leaf
+    int32_t prim;  // leaf: index into the caller's Hittable array
+};
+
+// BoundingBoxTree.make (RayTracing/BoundingBoxTree.fs:9-43): median split on box.Min[axis], axis by
+// minimum volume(L)+volume(R); leaves hold one object.  `prims` are indices of bounded objects in
+// array order (Scene.fs:16-22).
+void build_reference_tree(const RtHittable *objs, const std::vector<int32_t> &prims, std::vector<HostNode> &out);
+
+// ---- device-side scene layout (what rtfs_device.cu uploads) --------------------------------------
+// Bounded spheres, in SAH leaf order.  16 B each, one 128-bit load.
+struct DSphere {
+    float cx, cy, cz, r;
+};
+// BVH2 node with both children's boxes inline: 64 B = four 128-bit loads.
+//   q0 = {l.min.x, l.min.y, l.min.z, l.max.x}
+//   q1 = {l.max.y, l.max.z, r.min.x, r.min.y}
+//   q2 = {r.min.z, r.max.x, r.max.y, r.max.z}
+//   q3 = {left, right, -, -} as int bits: >= 0 internal node index, < 0 leaf holding sphere ~idx
+struct DNode {
+    float l_mn[3], l_mx[3];
+    float r_mn[3], r_mx[3];
+    int32_t left, right;
+    int32_t pad0, pad1;
+};
+static_assert(sizeof(DNode) == 64, "DNode must be 64 bytes");
+
+// Per-primitive material record, 32 B = two 128-bit loads.  Index = device primitive id.
+struct DMaterial {
+    double albedo;      // FP64 so that Pixel.darken's round-half-even is bit-exact (Pixel.fs:144-151)
+    float p0;           // fuzz (FUZZED) | ior (DIELECTRIC, GLASS) | cap threshold cx + 0.75 r (LIGHT_SOURCE_CAP)
+    float p1;           // prob (DIELECTRIC)
+    uint32_t style_rgb; // style << 24 | r << 16 | g << 8 | b
+    int32_t texture;    // index into textures, -1: constant colour
+    uint32_t flags;     // bit0: flipped (radius < 0, Sphere.fs:321); bit1: plane
+    int32_t host_index; // index into the caller's Hittable array
+};
+static_assert(sizeof(DMaterial) == 32, "DMaterial must be 32 bytes");
+
+// Unbounded objects (UnboundedSphere, InfinitePlane), tested linearly after the tree (Scene.fs:77-86).
+// Geometry is kept in FP64: the translation o - c and the c-term of the quadratic are evaluated in
+// FP64 on the device because these spheres are typically huge (r = 1000, 2000) and FP32 cancels.
+struct DUnbounded {
+    double p[3];   // centre / point on plane
+    double r2;     // radius^2 (sphere)
+    float n[3];    // plane normal
+    float r;       // signed radius (sphere)
+    int32_t shape; // RT_SHAPE_UNBOUNDED_SPHERE | RT_SHAPE_INFINITE_PLANE
+    int32_t pad[3];
+};
+static_assert(sizeof(DUnbounded) == 64, "DUnbounded must be 64 bytes");
+
+struct DTexture {
+    int32_t kind;
+    uint32_t rgb; // r << 16 | g << 8 | b
+    int32_t w, h;
+    unsigned long long tex; // cudaTextureObject_t (uchar4, point sampling, unnormalised coords)
+    int32_t even, odd;
+    float grid;
+    float cx, cy, cz, inv_radius;
+    int32_t pad[3];
+};
+static_assert(sizeof(DTexture) == 64, "DTexture must be 64 bytes");
+
+// Reference-topology tree for the exhaustive-DFS conformance traversal (F12).
+struct DRefNode {
+    float mn[3], mx[3];
+    int32_t right; // -1 leaf
+    int32_t prim;  // leaf: device primitive id, -1 if the object is not representable (never)
+};
+static_assert(sizeof(DRefNode) == 32, "DRefNode must be 32 bytes");
+
+struct HostSceneLayout {
+    // device primitive ids: [0, n_bounded) bounded spheres in SAH leaf order, then unbounded in array order
+    std::vector<DSphere> spheres;
+    std::vector<DNode> nodes;
+    std::vector<DMaterial> materials; // n_bounded + n_unbounded
+    std::vector<DUnbounded> unbounded;
+    std::vector<DRefNode> ref_nodes;
+    std::vector<int32_t> device_id_of; // caller's Hittable index -> device primitive id (-1: never hit, F16)
+    int32_t n_bounded = 0;
+    int32_t root_is_leaf = 0;
+    int32_t max_depth = 0;
+};
+
+// SAH BVH2 over the bounded spheres with radius >= 0 (a bounded sphere with negative radius has an
+// inverted box and is never hit in the reference, F16).  Fills layout.spheres/nodes and the bounded
+// part of layout.materials; also exports the tree in HostNode form for inspection.
+void build_device_layout(const RtHittable *objs, int32_t n_objs, const std::vector<HostNode> &ref_tree,
+                         HostSceneLayout &layout, std::vector<HostNode> &sah_tree_out);
+
+} // namespace rtfs
+
+// The opaque scene handle.
+struct RtScene {
+    std::vector<RtHittable> objects;
+    std::vector<RtTexture> textures;
+    std::vector<std::vector<uint8_t>> texture_pixels;
+    std::vector<rtfs::HostNode> ref_tree, sah_tree;
+    rtfs::HostSceneLayout layout;
+    int32_t device = -1;
+    void *dev = nullptr; // rtfs_device.cu: DeviceScene*
+};
+
+// implemented in rtfs_device.cu
+namespace rtfs {
+int device_scene_upload(RtScene *scene);
+void device_scene_free(RtScene *scene);
+size_t device_scene_bytes(const RtScene *scene);
+} // namespace rtfs
