@@ -123,8 +123,12 @@ typedef struct RtRenderOpts {
     int32_t adaptive; /* 1: the reference's early-out rule (Scene.fs:172-194); 0: always spp samples */
     int32_t mode;     /* RtMode                                                                  */
     int32_t gamma;    /* rt_render only: 1 = apply PixelOutput.correct (ImageOutput.fs:11-18) on the device */
-    int32_t _reserved;
+    int32_t flags;    /* RT_FLAG_* bits                                                           */
 } RtRenderOpts;
+
+/* RtRenderOpts.flags */
+#define RT_FLAG_COUNTERS 1 /* also count the device traversal's box / primitive tests (slower kernel variant) */
+#define RT_FLAG_NO_SMEM 2  /* read the BVH from global memory even when it would fit in shared memory      */
 
 typedef struct RtStats {
     uint64_t paths;     /* traceOnce calls (Scene.fs:118)                                        */
@@ -196,9 +200,21 @@ int rt_render(RtScene *scene, const RtCamera *camera, int32_t max_width_coord,
               int32_t max_height_coord, const RtRenderOpts *opts, uint8_t *rgb_out,
               int32_t *sums_out, RtStats *stats);
 
-/* Same frame split over `n_devices` GPUs of this process: replicated scene, sample-index split,
- * one ncclAllReduce(int32 sum) of the PixelStats buffer, finalize on device 0.
- * Results are bit-identical for every n_devices (integer sums keyed by sample index). */
+/* The same frame split over the GPUs of this process (the F# host is one process): replicated scene,
+ * sample-index split (Scene.fs:191-192 shared out by sample index), probe tiles shared out by tile.
+ * The devices exchange flags and sums through NVLink peer memory inside the kernels that consume them
+ * (no separate collective): the last kernel sums every device's PixelStats buffer for its slice of the
+ * pixels with peer loads, divides (Pixel.fs:103-108), applies gamma and stores RGB8 to pinned host
+ * memory.  Results are bit-identical for every device count (integer sums keyed by sample index).
+ * All devices must have peer access to one another (RT_ERR_UNSUPPORTED otherwise). */
+typedef struct RtMulti RtMulti;
+int rt_multi_create(const RtHittable *objects, int32_t n_objects, const RtTexture *textures,
+                    int32_t n_textures, const int32_t *devices, int32_t n_devices, RtMulti **out);
+int rt_multi_render(RtMulti *multi, const RtCamera *camera, int32_t max_width_coord,
+                    int32_t max_height_coord, const RtRenderOpts *opts, uint8_t *rgb_out,
+                    int32_t *sums_out, RtStats *stats);
+void rt_multi_destroy(RtMulti *multi);
+/* create + render + destroy in one call */
 int rt_render_multi(const RtHittable *objects, int32_t n_objects, const RtTexture *textures,
                     int32_t n_textures, const int32_t *devices, int32_t n_devices,
                     const RtCamera *camera, int32_t max_width_coord, int32_t max_height_coord,
@@ -221,6 +237,10 @@ int rt_device_probe(RtScene *scene, const RtCamera *camera, int32_t max_width_co
 int rt_device_main(RtScene *scene, const RtCamera *camera, int32_t max_width_coord,
                    int32_t max_height_coord, const RtRenderOpts *opts, int32_t rank, int32_t world,
                    int32_t *d_stats, const uint8_t *d_flags, void *stream, RtStats *stats);
+/* Work counters of this scene accumulated since its last rt_device_probe call: paths, rays, (with
+ * RT_FLAG_COUNTERS) box_tests / prim_tests; pixels_early_out holds the number of pixels that went ON to
+ * phase 2.  One small device->host copy and a synchronisation of `stream`; call it outside timed regions. */
+int rt_device_counters(RtScene *scene, void *stream, RtStats *stats);
 /* PixelStats.mean (Pixel.fs:103-108) + optional PixelOutput.correct: d_stats (after the sum
  * all-reduce) -> d_rgb rows*cols*3. */
 int rt_device_finalize(int32_t device, const int32_t *d_stats, int32_t n_pixels, int32_t gamma,
@@ -237,7 +257,10 @@ int rt_test_sphere_hit(int32_t device, int32_t n, const double *origin, const do
 /* InfinitePlane.intersection (InfinitePlane.fs:125-136). */
 int rt_test_plane_hit(int32_t device, int32_t n, const double *origin, const double *dir,
                       const double *point, const double *normal, double *t_out);
-/* BoundingBox.hits with inverseDirections (BoundingBox.fs:25-94). */
+/* BoundingBox.hits with inverseDirections (BoundingBox.fs:25-94): the decision-exact slab test that the
+ * reference-order traversal (rt_test_hit_object traversal = 1) runs.  The render traversal uses a
+ * conservative variant of it (padded, culled by the best hit); that one is covered by
+ * rt_test_hit_object traversal = 0. */
 int rt_test_aabb_hit(int32_t device, int32_t n, const double *origin, const double *dir,
                      const double *box_min, const double *box_max, uint8_t *hit_out);
 /* Scene.hitObject (Scene.fs:62-91).  prim_out = index into the caller's Hittable array or -1;

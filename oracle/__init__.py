@@ -300,6 +300,13 @@ class Scene:
         return rgb, stats, cn.as_dict(), done
 
 
+def render_split(scene, cam, max_w, max_h, seed, adaptive, phase, rank, world, stats, flags):
+    """One rank's share of one phase of the sample-split frame (orc_render_split); stats/flags are updated in place."""
+    assert stats.dtype == np.int32 and flags.dtype == np.uint8 and stats.flags["C_CONTIGUOUS"] and flags.flags["C_CONTIGUOUS"]
+    lib().orc_render_split(scene._ptr, C.byref(cam), C.c_int(max_w), C.c_int(max_h), C.c_uint64(seed), C.c_int(int(adaptive)),
+                           C.c_int(phase), C.c_int(rank), C.c_int(world), _vp(stats), _vp(flags))
+
+
 def sphere_reflection_direct(style, albedo, tex_colour, ior, prob, fuzz, centre, radius, o, d, strike, colour_in,
                              uniforms):
     """Sphere.reflection called with explicit parameters, as TestSphere.fs:52-152 calls it."""

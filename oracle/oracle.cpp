@@ -1262,4 +1262,55 @@ int orc_render(const OrcScene *s, const RtCamera *cam, int max_w, int max_h, uin
     return int(row_list.size());
 }
 
+// The sample-split decomposition of Scene.renderPixel that the multi-GPU path uses,
+// restated on the CPU so that "sum over ranks == unsplit render" can be checked without GPUs.
+//   phase 1: rank r probes the 8x4 tiles t with t mod world == r: the first 2*firstTrial+1 samples of
+//            renderPixel (Scene.fs:172-182) go into stats, flags[p] = 1 where the two means differ (:183-188);
+//   phase 2: for every flagged pixel, rank r adds the samples n_probe + r + j*world < spp (:191-192).
+// With adaptive = 0 phase 1 only raises flags (rank 0) and phase 2 shares out all spp samples.
+// The caller sums stats over ranks and takes the maximum of flags between the phases.
+void orc_render_split(const OrcScene *s, const RtCamera *cam, int max_w, int max_h, uint64_t seed, int adaptive, int phase,
+                      int rank, int world, int32_t *stats, uint8_t *flags) {
+    const int rows = 2 * max_h + 1, cols = 2 * max_w + 1;
+    const int tiles_x = (cols + 7) / 8;
+    const int spp = cam->samples_per_pixel;
+    const int first_trial = std::min(5, spp / 2);
+    const int n_probe = adaptive ? 2 * first_trial + 1 : 0;
+    const int sample_end = adaptive ? std::max(n_probe, spp) : spp;
+    Counters cn;
+    Rng rng;
+    rng.kind = Rng::COUNTER;
+    rng.seed = seed;
+    auto trace = [&](int row_idx, int col_idx, int sample, PixelStats &st) {
+        rng.pixel = uint32_t(row_idx * cols + col_idx);
+        rng.sample = uint32_t(sample);
+        trace_once(s->sc, rng, *cam, max_w, max_h, max_h - row_idx - 1, col_idx - max_w, st, cn);
+    };
+    for (int row_idx = 0; row_idx < rows; ++row_idx) {
+        for (int col_idx = 0; col_idx < cols; ++col_idx) {
+            const size_t p = size_t(row_idx) * cols + col_idx;
+            const int tile = (row_idx / 4) * tiles_x + col_idx / 8;
+            if (phase == 1) {
+                if (!adaptive) {
+                    if (rank == 0) flags[p] = 1;
+                    continue;
+                }
+                if (tile % world != rank) continue;
+                PixelStats st;
+                for (int i = 0; i <= first_trial; ++i) trace(row_idx, col_idx, i, st);
+                Pixel old_mean = st.mean();
+                for (int i = 1; i <= first_trial; ++i) trace(row_idx, col_idx, first_trial + i, st);
+                Pixel new_mean = st.mean();
+                stats[4 * p] = st.r; stats[4 * p + 1] = st.g; stats[4 * p + 2] = st.b; stats[4 * p + 3] = st.count;
+                flags[p] = (pixel_difference(new_mean, old_mean) != 0 && sample_end > n_probe) ? 1 : 0;
+            } else {
+                if (!flags[p]) continue;
+                PixelStats st;
+                for (int smp = n_probe + rank; smp < sample_end; smp += world) trace(row_idx, col_idx, smp, st);
+                stats[4 * p] += st.r; stats[4 * p + 1] += st.g; stats[4 * p + 2] += st.b; stats[4 * p + 3] += st.count;
+            }
+        }
+    }
+}
+
 } // extern "C"

@@ -37,6 +37,9 @@ RT_TEX_CHECKERED = 2
 RT_MODE_MEGAKERNEL = 0
 RT_MODE_WAVEFRONT = 1
 
+RT_FLAG_COUNTERS = 1
+RT_FLAG_NO_SMEM = 2
+
 RT_BVH_SAH = 0
 RT_BVH_REFERENCE = 1
 
@@ -95,7 +98,7 @@ class RtRenderOpts(C.Structure):
         ("adaptive", C.c_int32),
         ("mode", C.c_int32),
         ("gamma", C.c_int32),
-        ("_reserved", C.c_int32),
+        ("flags", C.c_int32),
     ]
 
 

@@ -1,0 +1,751 @@
+// rtfs_core.cuh — the device functions of the render path: counter RNG, vector algebra, integer
+// colour, camera ray generation, sphere / plane / box intersection, BVH traversal, scatter and
+// texture lookup.  Everything the render kernels and the conformance kernels execute lives here, so
+// that a conformance entry point runs exactly the function the render kernel runs.
+//
+// Arithmetic: FP32, except (a) Pixel.darken's product (FP64, so that .NET's round-half-to-even is
+// reproduced bit-for-bit), (b) the unbounded objects (huge spheres, planes), whose quadratic is
+// evaluated in FP64 because |o-c|^2 - r^2 cancels catastrophically in FP32 for r ~ 1000.
+//
+// Self-intersection.  The reference rejects the t ~ 0 root of a ray that starts on a surface with the
+// absolute test t > 1e-8, which works in FP64 (strike points lie within ~1e-13 of the surface) and
+// cannot work in FP32 (~1e-6).  A ray therefore carries the id of the primitive it left (`last`), and
+// the test against that primitive uses the exact on-surface form (c = 0 => roots 0 and -2b): the same
+// decisions as the reference makes, without the cancellation.  See DESIGN.md §"FP32 and 1e-8".
+#pragma once
+#include "rtfs_internal.h"
+
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#ifndef RTFS_HD
+#define RTFS_HD __device__ __forceinline__
+#endif
+
+namespace rtfs {
+
+constexpr float kTolF = 1e-8f;   // Float.tolerance, RayTracing/Float.fs:80
+constexpr double kTolD = 1e-8;
+constexpr uint32_t kWhite = 0x00FFFFFFu, kBlack = 0u, kHotPink = (205u << 16) | (105u << 8) | 180u; // Pixel.fs:18-66
+constexpr int kNoPrim = -1;
+constexpr float kNoHitT = 3.402823466e38f; // "bestFloat = infinity" (Scene.fs:65) as the largest finite float
+
+// ---- Float.compare, Float.fs:88-96 ------------------------------------------------------------
+enum Cmp { CMP_GREATER = 0, CMP_EQUAL = 1, CMP_LESS = 2 };
+RTFS_HD Cmp fcmp(float a, float b) { return (fabsf(a - b) < kTolF) ? CMP_EQUAL : (a < b ? CMP_LESS : CMP_GREATER); }
+RTFS_HD Cmp fcmp(double a, double b) { return (fabs(a - b) < kTolD) ? CMP_EQUAL : (a < b ? CMP_LESS : CMP_GREATER); }
+
+// ---- vectors (Point.fs:17-100) ------------------------------------------------------------------
+RTFS_HD float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
+RTFS_HD float3 operator+(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+RTFS_HD float3 operator-(float3 a, float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+RTFS_HD float3 operator*(float s, float3 a) { return f3(s * a.x, s * a.y, s * a.z); }
+RTFS_HD float3 operator-(float3 a) { return f3(-a.x, -a.y, -a.z); }
+RTFS_HD float dot(float3 a, float3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
+RTFS_HD float3 fma3(float s, float3 a, float3 b) { return f3(fmaf(s, a.x, b.x), fmaf(s, a.y, b.y), fmaf(s, a.z, b.z)); }
+// Vector.unitise (Point.fs:28-35) / Ray.overwriteWithMake (Ray.fs:11-24): fails iff |v.v| < 1e-8
+RTFS_HD bool unitise(float3 v, float3 &out) {
+    float d = dot(v, v);
+    if (fabsf(d) < kTolF) return false;
+    out = rsqrtf(d) * v;
+    // one Newton step is not needed: rsqrtf is 2 ulp; renormalisation error stays ~1e-7
+    return true;
+}
+
+struct D3 {
+    double x, y, z;
+};
+RTFS_HD D3 d3(float3 a) { return D3{double(a.x), double(a.y), double(a.z)}; }
+RTFS_HD D3 operator-(D3 a, D3 b) { return D3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+RTFS_HD double dot(D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+
+// ---- counter RNG ---------------------------------------------------------------------------------
+// Philox4x32-10 keyed by the frame seed, counter = (pixel, sample, bounce, retry).  Replaces the
+// reference's shared, time-seeded xorshift producers (Float.fs:13-76, Scene.fs:205).  One block gives
+// the 1-3 uniforms a bounce consumes; `retry` advances on every further block.
+RTFS_HD uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return c;
+}
+// FloatProducer's toDouble (Float.fs:29): w / (2^32 - 1) in [0, 1] inclusive.  In FP32 1/(2^32-1)
+// rounds to 2^-32 and float(0xFFFFFFFF) = 2^32, so the range is preserved.
+RTFS_HD float u01(uint32_t w) { return __uint2float_rn(w) * 2.3283064365386963e-10f; }
+
+struct CounterRng {
+    uint32_t k0, k1, pixel, sample, bounce, retry;
+    RTFS_HD float4 next() {
+        uint4 w = philox4x32_10(make_uint4(pixel, sample, bounce, retry), k0, k1);
+        ++retry;
+        return make_float4(u01(w.x), u01(w.y), u01(w.z), u01(w.w));
+    }
+};
+// explicit uniforms for the conformance entry points: four values, rotated by one per block
+struct ExplicitRng {
+    float u[4];
+    int rot;
+    RTFS_HD float4 next() {
+        float4 r = make_float4(u[rot & 3], u[(rot + 1) & 3], u[(rot + 2) & 3], u[(rot + 3) & 3]);
+        ++rot;
+        return r;
+    }
+};
+
+// UnitVector.random, Point.fs:49-59: cube-normalised (F4), retry only when |v|^2 < 1e-8
+template <class Rng>
+RTFS_HD float3 unit_random(Rng &rng) {
+    for (;;) {
+        float4 u = rng.next();
+        float3 v = f3(2.0f * u.x - 1.0f, 2.0f * u.y - 1.0f, 2.0f * u.z - 1.0f);
+        float3 out;
+        if (unitise(v, out)) return out;
+    }
+}
+
+// ---- colour (Pixel.fs:136-151) --------------------------------------------------------------------
+// colours are packed r << 16 | g << 8 | b
+RTFS_HD uint32_t div255(uint32_t x) { return (x * 0x8081u) >> 23; } // exact for x < 65536
+RTFS_HD uint32_t combine(uint32_t a, uint32_t b) {                  // Pixel.combine: (a * b) / 255, truncating
+    uint32_t r = div255(((a >> 16) & 255u) * ((b >> 16) & 255u));
+    uint32_t g = div255(((a >> 8) & 255u) * ((b >> 8) & 255u));
+    uint32_t bl = div255((a & 255u) * (b & 255u));
+    return (r << 16) | (g << 8) | bl;
+}
+RTFS_HD uint32_t darken(double albedo, uint32_t p) { // Pixel.darken: Math.Round (half to even) of a double product
+    uint32_t r = uint32_t(__double2int_rn(double((p >> 16) & 255u) * albedo)) & 255u;
+    uint32_t g = uint32_t(__double2int_rn(double((p >> 8) & 255u) * albedo)) & 255u;
+    uint32_t b = uint32_t(__double2int_rn(double(p & 255u) * albedo)) & 255u;
+    return (r << 16) | (g << 8) | b;
+}
+
+// ---- camera (Scene.fs:129-144) ----------------------------------------------------------------------
+struct DevCamera {
+    float ox, oy, oz;    // View.Origin
+    float cx, cy, cz;    // ViewportXAxis.Origin - View.Origin (subtracted on the host in FP64)
+    float xx, xy, xz;    // ViewportXAxis.Vector
+    float yx, yy, yz;    // ViewportYAxis.Vector
+    float sx, sy;        // ViewportWidth / maxWidthCoord, ViewportHeight / maxHeightCoord
+    int32_t max_w, max_h, rows, cols;
+    int32_t spp, depth;
+};
+// row / col are the signed coordinates renderPixel receives.  Returns false where Ray.make' would fail.
+RTFS_HD bool camera_ray(const DevCamera &c, int row, int col, float r1, float r2, float3 &o, float3 &d) {
+    float landing = (float(col) + r1) * c.sx;
+    float walk = (float(row) + r2) * c.sy;
+    float3 v = f3(fmaf(walk, c.yx, fmaf(landing, c.xx, c.cx)), fmaf(walk, c.yy, fmaf(landing, c.xy, c.cy)),
+                  fmaf(walk, c.yz, fmaf(landing, c.xz, c.cz)));
+    o = f3(c.ox, c.oy, c.oz);
+    return unitise(v, d);
+}
+
+// ---- BoundingBox.hits with inverseDirections (BoundingBox.fs:25-94) -----------------------------------
+// Decision-exact restatement: same comparison order, same +-inf / NaN behaviour (a NaN from 0 * inf
+// fails every comparison and so leaves tMin / tMax unchanged).  No early return is needed: the bail-outs
+// have no side effects, so evaluating all three axes and combining the predicates is equivalent.
+RTFS_HD bool aabb_hits_ref(float3 inv, float3 o, const float mn[3], const float mx[3]) {
+    float t_min = -CUDART_INF_F, t_max = CUDART_INF_F;
+    float t0 = (mn[0] - o.x) * inv.x, t1 = (mx[0] - o.x) * inv.x;
+    if (inv.x < 0.0f) { float s = t0; t0 = t1; t1 = s; }
+    t_min = (t0 > t_min) ? t0 : t_min;
+    t_max = (t1 < t_max) ? t1 : t_max;
+    bool ok = !(t_max < t_min || 0.0f >= t_max);
+    t0 = (mn[1] - o.y) * inv.y; t1 = (mx[1] - o.y) * inv.y;
+    if (inv.y < 0.0f) { float s = t0; t0 = t1; t1 = s; }
+    t_min = (t0 > t_min) ? t0 : t_min;
+    t_max = (t1 < t_max) ? t1 : t_max;
+    ok = ok && !(t_max < t_min || 0.0f >= t_max);
+    t0 = (mn[2] - o.z) * inv.z; t1 = (mx[2] - o.z) * inv.z;
+    if (inv.z < 0.0f) { float s = t0; t0 = t1; t1 = s; }
+    t_min = (t0 > t_min) ? t0 : t_min;
+    t_max = (t1 < t_max) ? t1 : t_max;
+    return ok && (t_max >= t_min && t_max >= 0.0f);
+}
+RTFS_HD float3 inverse_directions(float3 d) { return f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z); }
+
+// Slab test of the render traversal: conservative (boxes are rounded outwards on the host, tMax is
+// padded by 2 ulp as in Ize, "Robust BVH Ray Traversal"), returns the entry distance for ordering and
+// culls against the best hit so far (a finite number: kNoHitT while nothing is hit, so that the empty box
+// {+inf, +inf} of a one-leaf tree is never entered).  It may accept a box the reference rejects or vice versa only for
+// rays within rounding of a box face; closest-hit results do not depend on it (checked by
+// rt_test_hit_object(traversal = 0) against the oracle).
+RTFS_HD bool slab_entry(float3 inv, float3 o, float mnx, float mny, float mnz, float mxx, float mxy, float mxz, float best_t,
+                        float &entry) {
+    float ax = (mnx - o.x) * inv.x, bx = (mxx - o.x) * inv.x;
+    float ay = (mny - o.y) * inv.y, by = (mxy - o.y) * inv.y;
+    float az = (mnz - o.z) * inv.z, bz = (mxz - o.z) * inv.z;
+    float t_near = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
+    float t_far = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)) * 1.0000003576278687f;
+    entry = t_near;
+    return t_near <= fminf(t_far, best_t);
+}
+// direction components are clamped away from zero so that inv stays finite (no 0 * inf = NaN in the slabs)
+RTFS_HD float3 safe_inverse(float3 d) {
+    const float tiny = 1e-30f;
+    float x = fabsf(d.x) < tiny ? copysignf(tiny, d.x) : d.x;
+    float y = fabsf(d.y) < tiny ? copysignf(tiny, d.y) : d.y;
+    float z = fabsf(d.z) < tiny ? copysignf(tiny, d.z) : d.z;
+    return f3(1.0f / x, 1.0f / y, 1.0f / z);
+}
+
+// ---- Sphere.firstIntersection (Sphere.fs:349-386) -------------------------------------------------------
+// FP32 form for the bounded spheres.  The discriminant is evaluated as r^2 - |oc - b d|^2 (Haines et al.,
+// "Precision Improvements for Ray/Sphere Intersection"), algebraically the reference's b^2 - (|oc|^2 - r^2)
+// for unit d.  Root selection follows the reference line by line.  `self`: the ray starts on this sphere.
+RTFS_HD bool sphere_hit(float3 o, float3 d, float4 s, bool self, float &t_out) {
+    float3 oc = f3(o.x - s.x, o.y - s.y, o.z - s.z);
+    float b = dot(d, oc);
+    if (self) { // c = 0: roots 0 and -2b; the reference keeps the one that is `positive`
+        float t = -2.0f * b;
+        t_out = t;
+        return t > kTolF;
+    }
+    float3 l = fma3(-b, d, oc);
+    float disc = fmaf(s.w, s.w, -dot(l, l));
+    float ip;
+    if (fabsf(disc) < kTolF) { // Float.compare disc 0 = Equal
+        ip = -b;
+    } else if (disc < 0.0f) {
+        return false;
+    } else {
+        float im = sqrtf(disc);
+        float i1 = im - b, i2 = -(b + im);
+        bool p1 = i1 > kTolF, p2 = i2 > kTolF;
+        if (p1 && p2)
+            ip = (fabsf(i1 - i2) < kTolF || i1 < i2) ? i1 : i2;
+        else if (p1)
+            ip = i1;
+        else if (p2)
+            ip = i2;
+        else
+            return false;
+    }
+    t_out = ip;
+    return ip > kTolF;
+}
+// FP64 form for unbounded spheres (o, d are the FP32 ray promoted exactly).  d is unit only to ~1e-7, so
+// the quadratic keeps its leading coefficient a = d.d: the strike point then lies on the sphere to FP64
+// accuracy, as it does in the reference.
+RTFS_HD bool sphere_hit_f64(D3 o, D3 d, const DUnbounded &s, bool self, double &t_out) {
+    D3 oc = o - D3{s.p[0], s.p[1], s.p[2]};
+    double a = dot(d, d);
+    double b = dot(d, oc) / a;
+    if (self) {
+        double t = -2.0 * b;
+        t_out = t;
+        return t > kTolD;
+    }
+    double c = (dot(oc, oc) - s.r2) / a;
+    double disc = b * b - c;
+    double ip;
+    if (fabs(disc) < kTolD) {
+        ip = -b;
+    } else if (disc < 0.0) {
+        return false;
+    } else {
+        double im = sqrt(disc);
+        double i1 = im - b, i2 = -(b + im);
+        bool p1 = i1 > kTolD, p2 = i2 > kTolD;
+        if (p1 && p2)
+            ip = (fabs(i1 - i2) < kTolD || i1 < i2) ? i1 : i2;
+        else if (p1)
+            ip = i1;
+        else if (p2)
+            ip = i2;
+        else
+            return false;
+    }
+    t_out = ip;
+    return ip > kTolD;
+}
+// InfinitePlane.intersection (InfinitePlane.fs:125-136), FP64 on the promoted FP32 ray
+RTFS_HD bool plane_hit_f64(D3 o, D3 d, const DUnbounded &p, bool self, double &t_out) {
+    if (self) return false; // numerator is 0 on the plane: t = 0 is never `positive`
+    D3 n{double(p.n[0]), double(p.n[1]), double(p.n[2])};
+    double den = dot(n, d);
+    if (fabs(den) < kTolD) return false;
+    double t = dot(n, D3{p.p[0], p.p[1], p.p[2]} - o) / den;
+    t_out = t;
+    return t > kTolD;
+}
+// FP32 forms used by the per-primitive conformance entry points on arbitrary (non-self) inputs
+RTFS_HD bool plane_hit(float3 o, float3 d, float3 p, float3 n, float &t_out) {
+    float den = dot(n, d);
+    if (fabsf(den) < kTolF) return false;
+    float t = dot(n, p - o) / den;
+    t_out = t;
+    return t > kTolF;
+}
+
+// ---- scene access ------------------------------------------------------------------------------------
+// The render kernels read the flattened BVH either from global memory through the read-only path
+// (128-bit __ldg) or from a copy staged in shared memory (128-bit LDS); the template parameter picks.
+struct SceneGlobal {
+    const uint4 *nodes;
+    const float4 *spheres;
+    const uint4 *mats;
+    const DUnbounded *unb;
+    const DTexture *tex;
+    int32_t n_nodes, n_bounded, n_unbounded, n_tex;
+};
+
+#ifdef __CUDACC__
+extern __shared__ uint4 rtfs_smem[];
+#endif
+
+template <bool SMEM>
+struct SceneAccess {
+    SceneGlobal g;
+    uint32_t s_nodes, s_spheres, s_mats; // offsets into rtfs_smem in uint4 units (SMEM only)
+    RTFS_HD uint4 node_q(int i, int q) const {
+#ifdef __CUDACC__
+        if (SMEM) return rtfs_smem[s_nodes + 4u * uint32_t(i) + uint32_t(q)];
+#endif
+        return __ldg(g.nodes + 4 * i + q);
+    }
+    RTFS_HD float4 sphere(int i) const {
+#ifdef __CUDACC__
+        if (SMEM) {
+            uint4 v = rtfs_smem[s_spheres + uint32_t(i)];
+            return make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
+        }
+#endif
+        return __ldg(g.spheres + i);
+    }
+    RTFS_HD uint4 mat_q(int i, int q) const {
+#ifdef __CUDACC__
+        if (SMEM) return rtfs_smem[s_mats + 2u * uint32_t(i) + uint32_t(q)];
+#endif
+        return __ldg(g.mats + 2 * i + q);
+    }
+};
+
+struct Hit {
+    float t;
+    int32_t prim; // device primitive id, kNoPrim: nothing hit
+    float3 strike;
+};
+
+struct TraversalCounters {
+    uint32_t box_tests, prim_tests;
+};
+
+// Scene.hitObject (Scene.fs:62-91) over the SAH tree: ordered, culled by the best hit so far.  The
+// closest hit does not depend on tree topology or visiting order (only exact ties in t do, F12), so the
+// result equals the reference's exhaustive left-then-right DFS.  Then the unbounded objects in array
+// order, which must win by Float.compare t^2 best^2 = Less (Scene.fs:77-86).
+template <bool SMEM, bool COUNT>
+RTFS_HD Hit closest_hit(const SceneAccess<SMEM> &sc, float3 o, float3 d, int last, TraversalCounters &cn) {
+    float best_t = kNoHitT;
+    int best = kNoPrim;
+    if (sc.g.n_bounded > 0) {
+        float3 inv = safe_inverse(d);
+        int stack[64];
+        int sp = 0;
+        int node = 0;
+        for (;;) {
+            if (node >= 0) {
+                uint4 q0 = sc.node_q(node, 0), q1 = sc.node_q(node, 1), q2 = sc.node_q(node, 2), q3 = sc.node_q(node, 3);
+                float tl, tr;
+                bool hl = slab_entry(inv, o, __uint_as_float(q0.x), __uint_as_float(q0.y), __uint_as_float(q0.z),
+                                     __uint_as_float(q0.w), __uint_as_float(q1.x), __uint_as_float(q1.y), best_t, tl);
+                bool hr = slab_entry(inv, o, __uint_as_float(q1.z), __uint_as_float(q1.w), __uint_as_float(q2.x),
+                                     __uint_as_float(q2.y), __uint_as_float(q2.z), __uint_as_float(q2.w), best_t, tr);
+                if (COUNT) cn.box_tests += 2;
+                int left = int(q3.x), right = int(q3.y);
+                if (hl && hr) {
+                    bool left_first = tl <= tr;
+                    stack[sp++] = left_first ? right : left;
+                    node = left_first ? left : right;
+                    continue;
+                }
+                if (hl) { node = left; continue; }
+                if (hr) { node = right; continue; }
+            } else {
+                int k = ~node;
+                float4 s = sc.sphere(k);
+                float t;
+                if (COUNT) cn.prim_tests += 1;
+                if (sphere_hit(o, d, s, k == last, t) && t < best_t) {
+                    best_t = t;
+                    best = k;
+                }
+            }
+            if (sp == 0) break;
+            node = stack[--sp];
+        }
+    }
+    Hit h;
+    h.strike = fma3(best_t, d, o);
+    if (sc.g.n_unbounded > 0) {
+        D3 od = d3(o), dd = d3(d);
+        double best_a = double(best_t) * double(best_t);
+        double best_td = 0.0;
+        int best_u = kNoPrim;
+        for (int i = 0; i < sc.g.n_unbounded; ++i) {
+            const DUnbounded &u = sc.g.unb[i];
+            double t;
+            bool self = (sc.g.n_bounded + i) == last;
+            bool hit = (u.shape == RT_SHAPE_INFINITE_PLANE) ? plane_hit_f64(od, dd, u, self, t) : sphere_hit_f64(od, dd, u, self, t);
+            if (COUNT) cn.prim_tests += 1;
+            if (hit) {
+                double a = t * t;
+                if (fcmp(a, best_a) == CMP_LESS) {
+                    best_a = a;
+                    best_td = t;
+                    best_u = sc.g.n_bounded + i;
+                }
+            }
+        }
+        if (best_u != kNoPrim) {
+            best = best_u;
+            best_t = float(best_td);
+            h.strike = f3(float(od.x + best_td * dd.x), float(od.y + best_td * dd.y), float(od.z + best_td * dd.z));
+        }
+    }
+    h.t = best_t;
+    h.prim = best;
+    return h;
+}
+
+// The reference's own traversal (Scene.fs:30-60, F12): exhaustive left-then-right DFS of the
+// reference-topology tree with the decision-exact slab test and no culling.  Conformance only.
+RTFS_HD Hit closest_hit_reference(const DRefNode *ref_nodes, int n_ref_nodes, const SceneGlobal &g, float3 o, float3 d, int last) {
+    float best_t = CUDART_INF_F;
+    int best = kNoPrim;
+    if (n_ref_nodes > 0) {
+        float3 inv = inverse_directions(d);
+        int stack[64];
+        int sp = 0;
+        int node = 0;
+        for (;;) {
+            const DRefNode nd = ref_nodes[node];
+            bool descend = false;
+            if (aabb_hits_ref(inv, o, nd.mn, nd.mx)) {
+                if (nd.right < 0) {
+                    if (nd.prim >= 0) {
+                        float t;
+                        if (sphere_hit(o, d, __ldg(g.spheres + nd.prim), nd.prim == last, t) && t * t < best_t * best_t) {
+                            best_t = t;
+                            best = nd.prim;
+                        }
+                    }
+                } else {
+                    stack[sp++] = nd.right;
+                    node = node + 1;
+                    descend = true;
+                }
+            }
+            if (descend) continue;
+            if (sp == 0) break;
+            node = stack[--sp];
+        }
+    }
+    Hit h;
+    h.strike = fma3(best_t, d, o);
+    D3 od = d3(o), dd = d3(d);
+    double best_a = double(best_t) * double(best_t);
+    for (int i = 0; i < g.n_unbounded; ++i) {
+        const DUnbounded &u = g.unb[i];
+        double t;
+        bool self = (g.n_bounded + i) == last;
+        bool hit = (u.shape == RT_SHAPE_INFINITE_PLANE) ? plane_hit_f64(od, dd, u, self, t) : sphere_hit_f64(od, dd, u, self, t);
+        if (hit && fcmp(t * t, best_a) == CMP_LESS) {
+            best_a = t * t;
+            best = g.n_bounded + i;
+            best_t = float(t);
+            h.strike = f3(float(od.x + t * dd.x), float(od.y + t * dd.y), float(od.z + t * dd.z));
+        }
+    }
+    h.t = best_t;
+    h.prim = best;
+    return h;
+}
+
+// ---- textures (Texture.fs:12-15, :50-67; Sphere.planeMapInverse Sphere.fs:55-61) ------------------------
+#ifndef RTFS_HOST_DEBUG
+RTFS_HD uint32_t fetch_texel(unsigned long long tex, int x, int y) {
+    uchar4 v = tex2D<uchar4>(cudaTextureObject_t(tex), float(x) + 0.5f, float(y) + 0.5f);
+    return (uint32_t(v.x) << 16) | (uint32_t(v.y) << 8) | uint32_t(v.z);
+}
+#endif
+RTFS_HD uint32_t texture_colour(const SceneGlobal &g, int tex, float3 p) {
+    DTexture t = g.tex[tex];
+    if (t.kind == RT_TEX_COLOUR) return t.rgb;
+    float3 q = t.inv_radius * f3(p.x - t.cx, p.y - t.cy, p.z - t.cz);
+    float theta = acosf(fminf(1.0f, fmaxf(-1.0f, -q.y)));
+    float phi = atan2f(-q.z, q.x) + CUDART_PI_F;
+    float u = phi / (2.0f * CUDART_PI_F), v = theta / CUDART_PI_F;
+    for (int guard = 0; guard < 8 && t.kind == RT_TEX_CHECKERED; ++guard) { // Texture.fs:56-62
+        float sine = sinf(t.grid * u) * sinf(t.grid * v);
+        t = g.tex[(fcmp(sine, 0.0f) == CMP_LESS) ? t.even : t.odd];
+    }
+    if (t.kind == RT_TEX_COLOUR) return t.rgb;
+    if (t.kind == RT_TEX_IMAGE) { // Texture.fs:63-67: truncating nearest lookup with the u flip
+        int x = int((1.0f - u) * float(t.w - 1));
+        int y = int(v * float(t.h - 1));
+        x = min(max(x, 0), t.w - 1);
+        y = min(max(y, 0), t.h - 1);
+        return fetch_texel(t.tex, x, y);
+    }
+    return kBlack;
+}
+
+// ---- scatter ----------------------------------------------------------------------------------------------
+struct Material {
+    double albedo;
+    float p0, p1;
+    uint32_t style, rgb;
+    int32_t texture;
+    uint32_t flags;
+    int32_t host_index;
+};
+template <bool SMEM>
+RTFS_HD Material load_material(const SceneAccess<SMEM> &sc, int prim) {
+    uint4 a = sc.mat_q(prim, 0), b = sc.mat_q(prim, 1);
+    Material m;
+    m.albedo = __hiloint2double(int(a.y), int(a.x));
+    m.p0 = __uint_as_float(a.z);
+    m.p1 = __uint_as_float(a.w);
+    m.style = b.x >> 24;
+    m.rgb = b.x & 0x00FFFFFFu;
+    m.texture = int(b.y);
+    m.flags = b.z;
+    m.host_index = int(b.w);
+    return m;
+}
+
+// Sphere.reflectWithoutFuzz (Sphere.fs:68-87) / InfinitePlane.pureOutgoing (InfinitePlane.fs:18-38).
+// With T = unit(d - (n.d) n) the reference's -(n.d) n + (T.d) T equals d - 2 (n.d) n; when the tangent
+// cannot be normalised (|d - (n.d) n|^2 < 1e-8: the ray runs along the normal) it flips the ray.
+RTFS_HD float3 reflect_dir(float3 n, float3 d) {
+    float nd = dot(n, d);
+    float3 tangent = fma3(-nd, n, d);
+    if (fabsf(dot(tangent, tangent)) < kTolF) return -d;
+    float3 r = fma3(-nd, n, tangent);
+    float3 out;
+    if (!unitise(r, out)) return -d; // unreachable: |r| = 1
+    return out;
+}
+// Sphere.refract (Sphere.fs:108-146)
+RTFS_HD float3 refract_dir(bool inside, float3 n, float3 d, float incoming_cos, float ior) {
+    float index = inside ? 1.0f / ior : ior;
+    float nd = dot(n, d);
+    float3 tangent = fma3(-nd, n, d);
+    float3 tu;
+    if (!unitise(tangent, tu)) return d; // parallel to the normal: straight through
+    float incoming_sin = sqrtf(fmaxf(0.0f, 1.0f - incoming_cos * incoming_cos));
+    float outgoing_sin = incoming_sin / index;
+    if (fcmp(outgoing_sin, 1.0f) == CMP_GREATER) return reflect_dir(n, d);
+    float outgoing_cos = sqrtf(fmaxf(0.0f, 1.0f - outgoing_sin * outgoing_sin));
+    float3 v = fma3(outgoing_sin, tu, (-outgoing_cos) * n);
+    float3 out;
+    if (!unitise(v, out)) return d;
+    return out;
+}
+
+enum ScatterResult { SCATTER_CONTINUE = 0, SCATTER_ABSORBED = 1, SCATTER_ERROR = 2 };
+
+// Hittable.Reflection (Hittable.fs:8-12) -> Sphere.reflection (Sphere.fs:150-300) /
+// InfinitePlane.reflection (InfinitePlane.fs:43-99).  On SCATTER_CONTINUE the ray (o, d) and the colour
+// are updated in place; on SCATTER_ABSORBED `colour` is the emitted result.
+template <bool SMEM, class Rng>
+RTFS_HD ScatterResult scatter(const SceneAccess<SMEM> &sc, int prim, int last, float3 &o, float3 &d, float3 strike, uint32_t &colour,
+                              Rng &rng, bool *inside_out) {
+    const Material m = load_material(sc, prim);
+    const bool is_plane = (m.flags & 2u) != 0;
+    if (is_plane) {
+        const DUnbounded &pl = sc.g.unb[prim - sc.g.n_bounded];
+        float3 n = f3(pl.n[0], pl.n[1], pl.n[2]);
+        if (inside_out) *inside_out = false;
+        switch (m.style) {
+        case RT_STYLE_LIGHT_SOURCE:
+            colour = combine(colour, m.texture < 0 ? m.rgb : texture_colour(sc.g, m.texture, strike));
+            return SCATTER_ABSORBED;
+        case RT_STYLE_FUZZED_REFLECTION: {
+            uint32_t nc = darken(m.albedo, combine(colour, m.rgb));
+            float3 pure = reflect_dir(n, d);
+            float3 out;
+            for (;;) {
+                float3 offset = unit_random(rng);
+                if (unitise(fma3(m.p0, offset, pure), out)) break;
+            }
+            colour = nc;
+            o = strike;
+            d = out;
+            return SCATTER_CONTINUE;
+        }
+        case RT_STYLE_LAMBERT_REFLECTION: {
+            float3 offset = unit_random(rng);
+            float3 out;
+            if (!unitise(n + offset, out)) return SCATTER_ERROR; // ValueOption.get throws, InfinitePlane.fs:86
+            colour = darken(m.albedo, combine(colour, m.rgb));
+            o = strike;
+            d = out;
+            return SCATTER_CONTINUE;
+        }
+        case RT_STYLE_PURE_REFLECTION:
+            colour = darken(m.albedo, combine(colour, m.rgb));
+            d = reflect_dir(n, d);
+            o = strike;
+            return SCATTER_CONTINUE;
+        default: return SCATTER_ERROR;
+        }
+    }
+
+    // ---- sphere prologue, Sphere.fs:162-182 (F10) ----
+    const bool flipped = (m.flags & 1u) != 0;
+    float3 n;
+    Cmp where;
+    float cx;
+    if (prim < sc.g.n_bounded) {
+        float4 s = sc.sphere(prim);
+        float3 v = f3(strike.x - s.x, strike.y - s.y, strike.z - s.z);
+        if (!unitise(v, n)) return SCATTER_ERROR; // Sphere.normal's ValueOption.get
+        float3 co = f3(s.x - o.x, s.y - o.y, s.z - o.z);
+        where = (prim == last) ? CMP_EQUAL : fcmp(dot(co, co), s.w * s.w);
+        cx = s.x;
+    } else {
+        const DUnbounded &u = sc.g.unb[prim - sc.g.n_bounded];
+        D3 c{u.p[0], u.p[1], u.p[2]};
+        D3 v = d3(strike) - c;
+        double vv = dot(v, v);
+        if (fabs(vv) < kTolD) return SCATTER_ERROR;
+        double f = 1.0 / sqrt(vv);
+        n = f3(float(v.x * f), float(v.y * f), float(v.z * f));
+        D3 co = c - d3(o);
+        where = (prim == last) ? CMP_EQUAL : fcmp(dot(co, co), u.r2);
+        cx = float(u.p[0]);
+    }
+    bool inside = false;
+    if (where != CMP_GREATER) {
+        if (!flipped) { inside = true; n = -n; }
+    } else if (flipped) {
+        inside = true;
+        n = -n;
+    }
+    if (inside_out) *inside_out = inside;
+
+    if (m.style == RT_STYLE_LIGHT_SOURCE) { // :185-189
+        colour = combine(colour, m.texture < 0 ? m.rgb : texture_colour(sc.g, m.texture, strike));
+        return SCATTER_ABSORBED;
+    }
+    if (m.style == RT_STYLE_LIGHT_SOURCE_CAP) { // :190-200; p0 = centre.x + (r - r / 4)
+        (void)cx;
+        colour = (fcmp(strike.x, m.p0) == CMP_GREATER) ? combine(m.rgb, colour) : kBlack;
+        return SCATTER_ABSORBED;
+    }
+    const uint32_t nc = darken(m.albedo, combine(colour, m.texture < 0 ? m.rgb : texture_colour(sc.g, m.texture, strike)));
+    switch (m.style) {
+    case RT_STYLE_LAMBERT_REFLECTION: { // :202-222
+        float3 out;
+        for (;;) {
+            float3 offset = unit_random(rng);
+            if (unitise(n + offset, out)) break;
+        }
+        d = out;
+        break;
+    }
+    case RT_STYLE_PURE_REFLECTION: // :224-233
+        d = reflect_dir(n, d);
+        break;
+    case RT_STYLE_FUZZED_REFLECTION: { // :235-246 with addFuzz :89-104 (a fuzzed ray into the surface is kept, F11)
+        float3 pure = reflect_dir(n, d);
+        float3 out;
+        for (;;) {
+            float3 offset = unit_random(rng);
+            if (unitise(fma3(m.p0, offset, pure), out)) break;
+        }
+        d = out;
+        break;
+    }
+    case RT_STYLE_DIELECTRIC: { // :248-267
+        float u = rng.next().x;
+        if (u > m.p1)
+            d = reflect_dir(n, d);
+        else
+            d = refract_dir(inside, n, d, dot(d, n), m.p0);
+        break;
+    }
+    case RT_STYLE_GLASS: { // :269-300
+        float incoming_cos = -dot(d, n);
+        float u = rng.next().x;
+        float refr = inside ? 1.0f / m.p0 : m.p0;
+        float param = (1.0f - refr) / (1.0f + refr);
+        param = param * param;
+        float x = 1.0f - incoming_cos;
+        float x2 = x * x;
+        float reflection_prob = param + (1.0f - param) * (x2 * x2 * x);
+        if (u < reflection_prob)
+            d = reflect_dir(n, d);
+        else
+            d = refract_dir(inside, n, d, incoming_cos, m.p0);
+        break;
+    }
+    default: return SCATTER_ERROR;
+    }
+    colour = nc;
+    o = strike;
+    return SCATTER_CONTINUE;
+}
+
+// ---- one path (Scene.traceOnce :118-155 + Scene.traceRay :93-114) as a state machine -------------------
+// `begin` starts a camera sample; `step` performs one hitObject + Reflection and reports whether the
+// path ended.  The render kernels call `step` from a single flat loop so that the lanes of a warp stay
+// converged on the traversal while their paths are at different bounces (path regeneration).
+struct PathState {
+    float3 o, d;
+    uint32_t colour;
+    int32_t last;
+    int32_t bounces;
+    CounterRng rng;
+};
+RTFS_HD bool path_begin(PathState &p, const DevCamera &cam, uint32_t k0, uint32_t k1, int row_idx, int col_idx, uint32_t sample) {
+    p.rng.k0 = k0;
+    p.rng.k1 = k1;
+    p.rng.pixel = uint32_t(row_idx * cam.cols + col_idx);
+    p.rng.sample = sample;
+    p.rng.bounce = 0;
+    p.rng.retry = 0;
+    float4 u = p.rng.next(); // rand.GetTwo (), Scene.fs:129
+    p.colour = kWhite;
+    p.last = kNoPrim;
+    p.bounces = 0;
+    int row = cam.max_h - row_idx - 1; // Scene.fs:219
+    int col = col_idx - cam.max_w;     // Scene.fs:226
+    return camera_ray(cam, row, col, u.x, u.y, p.o, p.d);
+}
+// returns true when the path is finished; `result` is then its Pixel
+template <bool SMEM, bool COUNT>
+RTFS_HD bool path_step(PathState &p, const SceneAccess<SMEM> &sc, int max_count, uint32_t &result, TraversalCounters &cn) {
+    Hit h = closest_hit<SMEM, COUNT>(sc, p.o, p.d, p.last, cn);
+    if (h.prim == kNoPrim) { // the ray goes off into the distance
+        result = kBlack;
+        return true;
+    }
+    p.rng.bounce = uint32_t(p.bounces + 1);
+    p.rng.retry = 0;
+    ScatterResult r = scatter(sc, h.prim, p.last, p.o, p.d, h.strike, p.colour, p.rng, (bool *)nullptr);
+    if (r == SCATTER_ABSORBED) {
+        result = p.colour;
+        return true;
+    }
+    if (r == SCATTER_ERROR) { // the reference throws here; unreachable on non-degenerate input
+        result = kBlack;
+        return true;
+    }
+    p.last = h.prim;
+    p.bounces += 1;
+    if (p.bounces > max_count) { // while bounces <= maxCount, Scene.fs:98; not done => HotPink :114
+        result = kHotPink;
+        return true;
+    }
+    return false;
+}
+
+} // namespace rtfs

@@ -1,0 +1,126 @@
+// rtfs_device.h — declarations shared by the device translation units of librtfs_b200.so.
+#pragma once
+#include "rtfs_core.cuh"
+
+#include <string>
+#include <vector>
+
+namespace rtfs {
+
+// ---------------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------------
+#define RT_CUDA(expr)                                                                                         \
+    do {                                                                                                      \
+        cudaError_t e__ = (expr);                                                                             \
+        if (e__ != cudaSuccess)                                                                               \
+            return fail(RT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));                    \
+    } while (0)
+
+inline int require_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return fail(RT_ERR_NO_DEVICE, "no CUDA device is visible: librtfs_b200 has no CPU fallback");
+    }
+    if (device < 0 || device >= n) return fail(RT_ERR_INVALID_ARGUMENT, "CUDA device ordinal out of range");
+    RT_CUDA(cudaSetDevice(device));
+    return RT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// device scene
+// ---------------------------------------------------------------------------------------------------
+enum CounterSlot { CN_PATHS = 0, CN_RAYS = 1, CN_BOX = 2, CN_PRIM = 3, CN_LIST = 4, CN_WORK_PROBE = 5, CN_WORK_MAIN = 6, CN_SLOTS = 8 };
+
+struct DeviceScene {
+    int device = 0;
+    SceneGlobal g{};
+    DRefNode *ref_nodes = nullptr;
+    int32_t n_ref_nodes = 0;
+    std::vector<cudaArray_t> arrays;
+    std::vector<cudaTextureObject_t> texobjs;
+    size_t bytes = 0;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    // frame workspace owned by the handle (rt_render)
+    size_t ws_pixels = 0;
+    int32_t *d_stats = nullptr;
+    uint8_t *d_flags = nullptr;
+    uint8_t *d_rgb = nullptr;
+    // per-call scratch (any entry point)
+    size_t list_pixels = 0;
+    uint32_t *d_list = nullptr;
+    unsigned long long *d_counters = nullptr;
+    unsigned long long *h_counters = nullptr; // pinned
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+
+constexpr int kTileW = 8, kTileH = 4; // a warp's 32 pixels
+constexpr int kBlockThreads = 256;
+
+struct FrameParams {
+    SceneGlobal g;
+    DevCamera cam;
+    uint32_t k0, k1;
+    int32_t rank, world;
+    int32_t tiles_x, tiles_y;
+    int32_t first_trial;  // min 5 (spp / 2), Scene.fs:172
+    int32_t n_probe;      // 2 * first_trial + 1
+    int32_t sample_begin; // first sample index of the main phase
+    int32_t sample_end;   // one past the last
+    int32_t chunk;        // samples per main-phase work item
+    int32_t adaptive;
+    int32_t *stats;       // rows*cols*4 {sumR, sumG, sumB, count}
+    uint8_t *flags;       // rows*cols
+    const uint32_t *list; // flagged pixel ids (main phase)
+    unsigned long long *counters;
+    // shared-memory staging
+    uint32_t s_nodes, s_spheres, s_mats, s_warp; // offsets in uint4 units
+};
+
+
+constexpr int kMaxDevices = 16;
+// where the main phase finds the probe flags: one buffer (single device, or already combined by the
+// caller's all-reduce), or one buffer per rank, each holding the flags of the tiles that rank probed
+struct FlagsView {
+    const uint8_t *by_rank[kMaxDevices];
+    int32_t world;
+};
+inline FlagsView single_flags(const uint8_t *p) {
+    FlagsView v{};
+    v.by_rank[0] = p;
+    v.world = 1;
+    return v;
+}
+
+int check_frame_args(const RtScene *scene, const RtCamera *camera, int max_w, int max_h, const RtRenderOpts *opts);
+void fill_frame(FrameParams &fp, DeviceScene *ds, const RtCamera &cam, int max_w, int max_h, const RtRenderOpts &opts, int rank, int world);
+int launch_probe(DeviceScene *ds, FrameParams fp, bool count, bool no_smem, cudaStream_t st, int *launches);
+int launch_main(DeviceScene *ds, FrameParams fp, const FlagsView &flags, bool count, bool no_smem, cudaStream_t st, int *launches);
+void read_counters(DeviceScene *ds, RtStats *stats, size_t n_pixels, bool adaptive);
+
+inline DevCamera make_dev_camera(const RtCamera &c, int max_w, int max_h) {
+    DevCamera d{};
+    d.ox = float(c.view_origin[0]); d.oy = float(c.view_origin[1]); d.oz = float(c.view_origin[2]);
+    d.cx = float(c.xaxis_origin[0] - c.view_origin[0]);
+    d.cy = float(c.xaxis_origin[1] - c.view_origin[1]);
+    d.cz = float(c.xaxis_origin[2] - c.view_origin[2]);
+    d.xx = float(c.xaxis_dir[0]); d.xy = float(c.xaxis_dir[1]); d.xz = float(c.xaxis_dir[2]);
+    d.yx = float(c.yaxis_dir[0]); d.yy = float(c.yaxis_dir[1]); d.yz = float(c.yaxis_dir[2]);
+    d.sx = float(c.viewport_width / double(max_w));
+    d.sy = float(c.viewport_height / double(max_h));
+    d.max_w = max_w;
+    d.max_h = max_h;
+    d.rows = 2 * max_h + 1; // Scene.fs:208-209
+    d.cols = 2 * max_w + 1;
+    d.spp = c.samples_per_pixel;
+    d.depth = c.bounce_depth;
+    return d;
+}
+
+
+} // namespace rtfs

@@ -359,7 +359,7 @@ void build_device_layout(const RtHittable *objs, int32_t n_objs, const std::vect
     }
     int n = int(b.prims.size());
     if (n == 1) {
-        // a single leaf: wrap it in a node whose right child is an empty (never hit) box
+        // a single leaf: wrap it in a node whose right child is the box {+inf, +inf}, which no ray enters
         L.nodes.push_back(DNode{});
         int32_t leaf = b.emit_leaf(0);
         DNode &nd = L.nodes[0];
@@ -367,7 +367,7 @@ void build_device_layout(const RtHittable *objs, int32_t n_objs, const std::vect
             nd.l_mn[a] = b.prims[0].mn[a];
             nd.l_mx[a] = b.prims[0].mx[a];
             nd.r_mn[a] = std::numeric_limits<float>::infinity();
-            nd.r_mx[a] = -std::numeric_limits<float>::infinity();
+            nd.r_mx[a] = std::numeric_limits<float>::infinity();
         }
         nd.left = leaf;
         nd.right = leaf;

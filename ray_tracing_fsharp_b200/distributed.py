@@ -1,0 +1,80 @@
+"""One frame shared out over ranks (one process per GPU): the sample-split of SURVEY.md §8e.
+
+    phase 1  rt_device_probe   rank r probes the tiles t with t mod world == r      (Scene.fs:172-188)
+             all_reduce(flags, MAX)                                                  [only if world > 1]
+    phase 2  rt_device_main    rank r adds samples n_probe + r + j*world of every flagged pixel (:191-192)
+             all_reduce(stats, SUM)   int32 {sumR, sumG, sumB, count} per pixel      [only if world > 1]
+    tail     rt_device_finalize  PixelStats.mean (+ gamma) -> RGB8                   (Pixel.fs:103-108)
+
+Integer sums keyed by sample index make the result independent of `world`.  The orchestration below is
+backend-agnostic: the product backend (`DeviceBackend`) runs the CUDA kernels on torch CUDA tensors and
+NCCL; tests/ drive the same function with a CPU backend over gloo to check the decomposition.
+"""
+import ctypes as C
+
+from . import abi, native
+
+
+def render_split_frame(backend, rank: int, world: int, all_reduce_max=None, all_reduce_sum=None):
+    """Runs the three steps above on `backend`; returns (stats, flags) after the reductions.
+    `all_reduce_max(flags)` / `all_reduce_sum(stats)` are in-place collectives (ignored when world == 1)."""
+    stats, flags = backend.alloc()
+    backend.probe(rank, world, stats, flags)
+    if world > 1:
+        all_reduce_max(flags)
+    backend.main(rank, world, stats, flags)
+    if world > 1:
+        all_reduce_sum(stats)
+    return stats, flags
+
+
+class DeviceBackend:
+    """rt_device_probe / rt_device_main / rt_device_finalize on torch CUDA tensors (current stream)."""
+
+    def __init__(self, scene: native.SceneHandle, camera: abi.RtCamera, max_w: int, max_h: int, seed: int = 0, adaptive: bool = True,
+                 flags: int = 0):
+        import torch
+        self.torch = torch
+        self.scene, self.camera, self.max_w, self.max_h = scene, camera, max_w, max_h
+        self.opts = abi.RtRenderOpts(seed, int(adaptive), abi.RT_MODE_MEGAKERNEL, 0, flags)
+        self.n_pixels = (2 * max_w + 1) * (2 * max_h + 1)
+        self.device = torch.device("cuda", scene.device)
+        self.launches = 0
+        self._stats = None
+        self._flags = None
+        self._rgb = None
+
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def alloc(self):
+        torch = self.torch
+        if self._stats is None:
+            self._stats = torch.empty((self.n_pixels, 4), dtype=torch.int32, device=self.device)
+            self._flags = torch.empty((self.n_pixels,), dtype=torch.uint8, device=self.device)
+            self._rgb = torch.empty((self.n_pixels, 3), dtype=torch.uint8, device=self.device)
+        self._stats.zero_()
+        self._flags.zero_()
+        return self._stats, self._flags
+
+    def probe(self, rank, world, stats, flags):
+        native.check(native.lib().rt_device_probe(self.scene.ptr, C.byref(self.camera), self.max_w, self.max_h, C.byref(self.opts), rank,
+                                                  world, C.c_void_p(stats.data_ptr()), C.c_void_p(flags.data_ptr()), self._stream(), None))
+        self.launches += 1 if self.opts.adaptive else 0
+
+    def main(self, rank, world, stats, flags):
+        native.check(native.lib().rt_device_main(self.scene.ptr, C.byref(self.camera), self.max_w, self.max_h, C.byref(self.opts), rank,
+                                                 world, C.c_void_p(stats.data_ptr()), C.c_void_p(flags.data_ptr()), self._stream(), None))
+        self.launches += 2  # compact + main
+
+    def finalize(self, stats, gamma=False):
+        native.check(native.lib().rt_device_finalize(self.scene.device, C.c_void_p(stats.data_ptr()), self.n_pixels, int(gamma),
+                                                     C.c_void_p(self._rgb.data_ptr()), self._stream()))
+        self.launches += 1
+        return self._rgb
+
+    def counters(self) -> abi.RtStats:
+        """Work counters (paths, rays, ...) of this rank since the last probe; synchronises the stream."""
+        out = abi.RtStats()
+        native.check(native.lib().rt_device_counters(self.scene.ptr, self._stream(), C.byref(out)))
+        return out

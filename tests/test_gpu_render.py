@@ -1,0 +1,231 @@
+"""Level-2 parity: rendered frames of the CUDA path against the CPU oracle, through the C ABI and
+the mirrored Scene.render surface.
+
+ (i)   same counter RNG on both sides: near-identical bytes (differences only where FP32 flips a decision);
+ (ii)  independent RNGs (oracle: the reference's xorshift128; GPU: Philox) at high spp: per-channel mean absolute
+       difference of the pre-gamma means under 3 sigma of the per-pixel estimator;
+ (iii) size-independent properties at full size: determinism, invariance under the sample split, integer
+       accumulator invariants, the early-out rule's count field, gamma == host LUT, P3 bytes.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle
+from helpers import oracle_camera, scene_pair, small_random_spheres
+from ray_tracing_fsharp_b200 import abi, native, sample_images
+from ray_tracing_fsharp_b200.domain import marshal
+from ray_tracing_fsharp_b200.scene import Camera, Image, ImageOutput, Scene
+
+pytestmark = pytest.mark.gpu
+
+
+def _small(config, max_w, max_h, spp):
+    spec = sample_images.CONFIGS[config]()
+    spec.max_width_coord, spec.max_height_coord, spec.spp = max_w, max_h, spp
+    return spec
+
+
+@pytest.mark.parametrize("config,max_w,max_h,spp", [("C1", 100, 56, 16), ("C2", 60, 40, 24), ("C3", 64, 36, 16), ("C4", 64, 36, 32)])
+def test_frame_matches_oracle_with_shared_rng(config, max_w, max_h, spp):
+    spec = _small(config, max_w, max_h, spp)
+    osc, dsc, cam = scene_pair(spec)
+    ref, ref_stats, counters, _ = osc.render(cam, max_w, max_h, seed=5, rng_mode=1, adaptive=True)
+    rgb, sums, stats = dsc.render(cam, max_w, max_h, seed=5, adaptive=True, want_sums=True)
+    assert rgb.shape == ref.shape == (2 * max_h + 1, 2 * max_w + 1, 3)  # F6
+    same_px = (rgb == ref).all(2)
+    assert same_px.mean() > 0.985, same_px.mean()
+    # the integer accumulators themselves: identical for almost every pixel, never far off
+    same_sums = (sums == ref_stats).all(2)
+    assert same_sums.mean() > 0.97, same_sums.mean()
+    assert np.array_equal(sums[..., 3] == spp, ref_stats[..., 3] == spp) or (sums[..., 3] != ref_stats[..., 3]).mean() < 0.01
+    assert abs(int(stats.paths) - counters["paths"]) <= 0.01 * counters["paths"]
+    assert abs(int(stats.rays) - counters["rays"]) <= 0.01 * counters["rays"]
+    assert np.abs(rgb.astype(int) - ref.astype(int)).mean() < 0.3
+
+
+def test_adaptive_rule_and_counts():
+    """F5: count is 2*firstTrial+1 where the two truncated means agree, else spp; spp < 11 gives 2*(spp/2)+1 samples."""
+    spec = _small("C1", 80, 45, 16)
+    osc, dsc, cam = scene_pair(spec)
+    rgb, sums, stats = dsc.render(cam, 80, 45, seed=1, adaptive=True, want_sums=True)
+    counts = np.unique(sums[..., 3])
+    assert set(counts.tolist()) <= {11, 16} and 11 in counts and 16 in counts
+    assert int(stats.pixels_early_out) == int((sums[..., 3] == 11).sum())
+    assert int(stats.paths) == int(sums[..., 3].sum())
+    # mean = truncating division of the integer sums (Pixel.fs:103-108)
+    assert np.array_equal(rgb, (sums[..., :3] // sums[..., 3:4]).astype(np.uint8))
+    for spp, expect in [(1, {1}), (4, {5}), (7, {7}), (10, {11}), (11, {11})]:
+        cam.samples_per_pixel = spp
+        _, s2, st2 = dsc.render(cam, 20, 11, seed=2, adaptive=True, want_sums=True)
+        assert set(np.unique(s2[..., 3]).tolist()) == expect, (spp, np.unique(s2[..., 3]))
+        ref, rs, _, _ = osc.render(cam, 20, 11, seed=2, rng_mode=1, adaptive=True)
+        assert np.array_equal(rs[..., 3], s2[..., 3])
+    cam.samples_per_pixel = 16
+    _, s3, st3 = dsc.render(cam, 80, 45, seed=1, adaptive=False, want_sums=True)
+    assert (s3[..., 3] == 16).all() and int(st3.paths) == 16 * s3.shape[0] * s3.shape[1] and st3.pixels_early_out == 0
+
+
+def test_shared_memory_and_global_memory_kernels_agree_bit_for_bit():
+    spec = small_random_spheres()
+    osc, dsc, cam = scene_pair(spec)
+    a, sa, _ = dsc.render(cam, spec.max_width_coord, spec.max_height_coord, seed=9, want_sums=True)
+    b, sb, _ = dsc.render(cam, spec.max_width_coord, spec.max_height_coord, seed=9, want_sums=True, flags=abi.RT_FLAG_NO_SMEM)
+    c, sc, stc = dsc.render(cam, spec.max_width_coord, spec.max_height_coord, seed=9, want_sums=True, flags=abi.RT_FLAG_COUNTERS)
+    assert np.array_equal(sa, sb) and np.array_equal(a, b)
+    assert np.array_equal(sa, sc) and stc.box_tests > 0 and stc.prim_tests > 0
+    d, sd, _ = dsc.render(cam, spec.max_width_coord, spec.max_height_coord, seed=10, want_sums=True)
+    assert not np.array_equal(sa, sd)  # the seed matters
+
+
+def test_hot_pink_when_the_bounce_budget_runs_out():
+    """F3: a path that is still alive after maxCount + 1 interactions is HotPink, a miss is Black."""
+    from ray_tracing_fsharp_b200.domain import Colour, Hittable, Pixel, Sphere, SphereStyle, Texture
+    # camera inside a mirror ball: no emitter can ever be reached
+    objs = [Hittable.Sphere(Sphere.make(SphereStyle.PureReflection(1.0, Texture.Colour(Colour.White)), (0.0, 0.0, 0.0), 5.0))]
+    hs, ts, keep = marshal(objs)
+    dsc = native.SceneHandle(hs, ts, 0, keepalive=keep)
+    cam = Camera.make_basic(4, 1.0, 1.0, (0.0, 0.0, 0.0), (0.0, 0.0, 1.0), (0.0, 1.0, 0.0))
+    cam.bounce_depth = 7
+    rgb, sums, stats = dsc.render(cam, 8, 8, seed=3, adaptive=False, want_sums=True)
+    assert (rgb == np.array([205, 105, 180], np.uint8)).all()
+    assert int(stats.rays) == int(stats.paths) * 8  # maxCount + 1 interactions
+    # empty scene: every ray escapes => Black
+    dsc2 = native.SceneHandle([], [], 0)
+    rgb2, _, st2 = dsc2.render(cam, 8, 8, seed=3, adaptive=False)
+    assert (rgb2 == 0).all() and int(st2.rays) == int(st2.paths)
+
+
+def test_statistical_parity_at_4096_spp():
+    """Independent RNGs: oracle with the reference's xorshift128, GPU with Philox; 4096 spp, adaptive off on both so
+    that every pixel is a 4096-sample estimator.  Per channel, MAD of the (pre-gamma, truncated) means must be under
+    3 * sigma-bar, sigma-bar = mean over pixels of sqrt(2 s^2 / N) (difference of two independent means)."""
+    for config, max_w, max_h in [("C1", 24, 13), ("C2", 24, 16), ("C4", 24, 13)]:
+        spec = _small(config, max_w, max_h, 4096)
+        osc, dsc, cam = scene_pair(spec)
+        ref, ref_stats, _, _ = osc.render(cam, max_w, max_h, seed=77, rng_mode=0, adaptive=False)
+        rgb, sums, _ = dsc.render(cam, max_w, max_h, seed=78, adaptive=False, want_sums=True)
+        n = 4096
+        mean_g = sums[..., :3] / n
+        mean_o = ref_stats[..., :3] / n
+        # per-sample variance bound from the mean alone: a byte-valued sample x in [0, 255] has s^2 <= m (255 - m);
+        # use the empirical variance of the GPU estimator from two half-runs instead, which is tighter
+        _, s_a, _ = dsc.render(cam, max_w, max_h, seed=79, adaptive=False, want_sums=True)
+        var_of_mean = ((sums[..., :3] - s_a[..., :3]) / n) ** 2 / 2.0  # unbiased estimate of Var(mean) per pixel
+        sigma_bar = np.sqrt(2.0 * var_of_mean.mean(axis=(0, 1)))        # difference of two independent means
+        mad = np.abs(mean_g - mean_o).mean(axis=(0, 1))
+        assert (mad < 3.0 * sigma_bar + 0.5).all(), (config, mad, sigma_bar)  # +0.5: both sides truncate to bytes
+        assert np.abs(rgb.astype(int) - ref.astype(int)).mean() < 1.5, config
+
+
+def test_scene_render_surface_and_ppm_bytes():
+    spec = _small("C1", 40, 22, 16)
+    cam = Camera.make_basic(spec.spp, spec.focal_length, spec.aspect_ratio, spec.origin, spec.view_direction, spec.view_up)
+    assert cam.bounce_depth == 150  # F7
+    cam.bounce_depth = spec.bounce_depth
+    scene = Scene.make(spec.objects, device=0)
+    ticks = []
+    total, image = Scene.render(ticks.append, lambda s: None, 40, 22, cam, scene, seed=11)
+    assert total == 45.0 and Image.row_count(image) == 45 and Image.col_count(image) == 81 and ticks == []  # lazy
+    pixels = Image.render(image)
+    assert len(ticks) == 45 and pixels.shape == (45, 81, 3)
+    # PPM bytes: the device result through the library's writer == the oracle's writer on the same pixels
+    assert ImageOutput.write_ppm(False, pixels) == oracle.ppm_format(pixels, False)
+    assert ImageOutput.write_ppm(True, pixels) == oracle.ppm_format(pixels, True)
+    # gamma on the device == PixelOutput.correct applied on the host
+    rgb_g, _, _ = scene.handle.render(cam, 40, 22, seed=11, gamma=True)
+    lut = np.array([oracle.gamma_correct(i) for i in range(256)], np.uint8)
+    assert np.array_equal(rgb_g, lut[pixels])
+    # and against the oracle's frame with the shared RNG
+    hs, ts, _ = marshal(spec.objects)
+    ref, _, _, _ = oracle.Scene(hs, ts).render(cam, 40, 22, seed=11, rng_mode=1, adaptive=True)
+    assert (pixels == ref).all(2).mean() > 0.985
+
+
+def test_sample_split_is_invariant_emulated_on_one_gpu():
+    """The multi-GPU decomposition run rank by rank on one device: summing the ranks' buffers reproduces the
+    single-rank frame bit for bit (integer sums keyed by sample index), for world = 1, 2, 3, 8."""
+    import torch
+    from ray_tracing_fsharp_b200.distributed import DeviceBackend, render_split_frame
+    spec = small_random_spheres()
+    osc, dsc, cam = scene_pair(spec)
+    max_w, max_h = spec.max_width_coord, spec.max_height_coord
+    _, base, _ = dsc.render(cam, max_w, max_h, seed=21, adaptive=True, want_sums=True)
+    n_pixels = base.shape[0] * base.shape[1]
+    for world in (1, 2, 3, 8):
+        backends = [DeviceBackend(dsc, cam, max_w, max_h, seed=21, adaptive=True) for _ in range(world)]
+        bufs = [b.alloc() for b in backends]
+        for r in range(world):
+            backends[r].probe(r, world, *bufs[r])
+        flags = torch.stack([f for _, f in bufs]).max(0).values.contiguous()  # all_reduce(MAX)
+        for r in range(world):
+            bufs[r][1].copy_(flags)
+            backends[r].main(r, world, *bufs[r])
+        total = torch.stack([s for s, _ in bufs]).sum(0).to(torch.int32).contiguous()  # all_reduce(SUM)
+        torch.cuda.synchronize()
+        assert np.array_equal(total.cpu().numpy().reshape(base.shape), base), world
+        rgb = backends[0].finalize(total).cpu().numpy().reshape(base.shape[0], base.shape[1], 3)
+        assert np.array_equal(rgb, (base[..., :3] // base[..., 3:4]).astype(np.uint8))
+    # non-adaptive split
+    _, base2, _ = dsc.render(cam, max_w, max_h, seed=22, adaptive=False, want_sums=True)
+    world = 4
+    backends = [DeviceBackend(dsc, cam, max_w, max_h, seed=22, adaptive=False) for _ in range(world)]
+    bufs = [b.alloc() for b in backends]
+    for r in range(world):
+        backends[r].probe(r, world, *bufs[r])
+    flags = torch.stack([f for _, f in bufs]).max(0).values.contiguous()
+    for r in range(world):
+        bufs[r][1].copy_(flags)
+        backends[r].main(r, world, *bufs[r])
+    total = torch.stack([s for s, _ in bufs]).sum(0).to(torch.int32)
+    assert np.array_equal(total.cpu().numpy().reshape(base2.shape), base2)
+
+
+def test_multi_device_frame_is_bit_identical():
+    n = native.device_count()
+    if n < 2:
+        pytest.skip("needs two GPUs with peer access")
+    spec = small_random_spheres()
+    osc, dsc, cam = scene_pair(spec)
+    hs, ts, keep = marshal(spec.objects)
+    rgb1, sums1, _ = dsc.render(cam, spec.max_width_coord, spec.max_height_coord, seed=31, want_sums=True)
+    for world in sorted({2, min(n, 4), n}):
+        m = native.MultiHandle(hs, ts, list(range(world)), keepalive=keep)
+        rgb, sums, stats = m.render(cam, spec.max_width_coord, spec.max_height_coord, seed=31, want_sums=True)
+        assert np.array_equal(sums, sums1) and np.array_equal(rgb, rgb1)
+        m.close()
+
+
+def test_full_size_properties_c2():
+    """BASELINE.json's full frame size (1201x801) at reduced spp: determinism, split invariance of the early-out
+    accounting, and the accumulator invariants.  (The 500 spp frame itself is what bench.py renders.)"""
+    spec = sample_images.random_spheres(spp=24)
+    hs, ts, keep = marshal(spec.objects)
+    dsc = native.SceneHandle(hs, ts, 0, keepalive=keep)
+    cam = oracle_camera(spec)
+    a, sa, sta = dsc.render(cam, 600, 400, seed=1, want_sums=True)
+    b, sb, stb = dsc.render(cam, 600, 400, seed=1, want_sums=True)
+    assert a.shape == (801, 1201, 3)
+    assert np.array_equal(sa, sb) and int(sta.rays) == int(stb.rays)                 # deterministic
+    assert set(np.unique(sa[..., 3]).tolist()) <= {11, 24}
+    assert int(sta.paths) == int(sa[..., 3].sum())
+    assert (sa[..., :3] <= 255 * sa[..., 3:4]).all() and (sa[..., :3] >= 0).all()
+    assert np.array_equal(a, (sa[..., :3] // sa[..., 3:4]).astype(np.uint8))
+    # the sky (light dome seen directly) is exactly its emitted colour and early-outs
+    assert (a[0, 0] == np.array([200, 200, 255], np.uint8)).all() and sa[0, 0, 3] == 11
+
+
+def test_errors_are_codes_not_crashes():
+    lib = native.lib()
+    cam = Camera.make_basic(4, 1.0, 1.0, (0.0, 0.0, 0.0), (0.0, 0.0, 1.0), (0.0, 1.0, 0.0))
+    dsc = native.SceneHandle([], [], 0)
+    opts = abi.RtRenderOpts(0, 1, 0, 0, 0)
+    out = np.zeros((3, 3, 3), np.uint8)
+    assert lib.rt_render(dsc.ptr, C.byref(cam), 0, 1, C.byref(opts), native.ptr(out), None, None) == abi.RT_ERR_INVALID_ARGUMENT
+    assert lib.rt_render(dsc.ptr, C.byref(cam), 1, 1, C.byref(opts), None, None, None) == abi.RT_ERR_INVALID_ARGUMENT
+    opts.mode = 7
+    assert lib.rt_render(dsc.ptr, C.byref(cam), 1, 1, C.byref(opts), native.ptr(out), None, None) == abi.RT_ERR_INVALID_ARGUMENT
+    assert b"mode" in lib.rt_last_error()
+    with pytest.raises(native.RtError):
+        native.SceneHandle([], [], 99)

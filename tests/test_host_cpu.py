@@ -1,0 +1,236 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol include/rtfs_b200.h declares, the
+ctypes mirror matches the header's struct layouts, the host logic (Camera.makeBasic, P3 writer, gamma, the two
+BVH builders, argument validation) agrees with the oracle, and the product package never touches the oracle."""
+import ctypes as C
+import os
+import re
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+import oracle
+from helpers import small_random_spheres
+from ray_tracing_fsharp_b200 import abi, native, sample_images
+from ray_tracing_fsharp_b200.domain import (Colour, Hittable, InfinitePlane, InfinitePlaneStyle, ParameterisedTexture, Pixel, Sphere,
+                                            SphereStyle, Texture, marshal)
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "rtfs_b200.h")
+
+
+def test_library_exports_every_declared_symbol():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    declared = set(re.findall(r"\b(rt_[a-z0-9_]+)\s*\(", text))
+    assert len(declared) >= 30
+    lib = native.lib()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} is declared in include/rtfs_b200.h but not exported by librtfs_b200.so"
+    assert declared == set(native.EXPORTS), declared ^ set(native.EXPORTS)
+    assert lib.rt_abi_version() == abi.RT_ABI_VERSION
+
+
+def test_ctypes_mirror_matches_header_layout():
+    src = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "rtfs_b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu\n", sizeof(RtTexture), sizeof(RtHittable), sizeof(RtCamera), sizeof(RtRenderOpts), sizeof(RtStats));
+  printf("%zu %zu %zu %zu\n", offsetof(RtTexture, rgb8), offsetof(RtTexture, map_radius), offsetof(RtHittable, texture), offsetof(RtCamera, samples_per_pixel));
+  printf("%zu %zu\n", offsetof(RtStats, kernel_ms), offsetof(RtStats, launches));
+  return 0; }
+'''
+    with tempfile.TemporaryDirectory() as td:
+        c = os.path.join(td, "s.c")
+        open(c, "w").write(src)
+        exe = os.path.join(td, "s")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        out = subprocess.check_output([exe], text=True).split()
+    got = [int(x) for x in out]
+    want = [C.sizeof(abi.RtTexture), C.sizeof(abi.RtHittable), C.sizeof(abi.RtCamera), C.sizeof(abi.RtRenderOpts), C.sizeof(abi.RtStats),
+            abi.RtTexture.rgb8.offset, abi.RtTexture.map_radius.offset, abi.RtHittable.texture.offset, abi.RtCamera.samples_per_pixel.offset,
+            abi.RtStats.kernel_ms.offset, abi.RtStats.launches.offset]
+    assert got == want
+
+
+@pytest.mark.parametrize("config", ["C1", "C2", "C3", "C4"])
+def test_camera_make_basic_matches_oracle(config):
+    spec = sample_images.CONFIGS[config]()
+    a = native.camera_make_basic(spec.spp, spec.focal_length, spec.aspect_ratio, spec.origin, spec.view_direction, spec.view_up)
+    b = oracle.camera_make_basic(spec.spp, spec.focal_length, spec.aspect_ratio, spec.origin, spec.view_direction, spec.view_up)
+    assert bytes(a) == bytes(b)
+    assert a.bounce_depth == 150
+    x, y, v = np.array(a.xaxis_dir), np.array(a.yaxis_dir), np.array(a.view_dir)
+    assert np.allclose(np.cross(x, y), v, atol=1e-12)  # X x Y = view
+
+
+def test_camera_make_basic_survey_check_values():
+    a = native.camera_make_basic(1, 10.0, 1.5, (13.0, 2.0, -3.0), tuple(-np.array([13.0, 2.0, -3.0]) / np.sqrt(182.0)), (0.0, 1.0, 0.0))
+    assert np.allclose(a.xaxis_dir, (0.224860, 0.0, 0.974391), atol=1e-6)
+    assert np.allclose(a.yaxis_dir, (-0.144453, 0.988950, 0.033335), atol=1e-6)
+    with pytest.raises(native.RtError):  # viewUp parallel to the view direction: the reference throws
+        native.camera_make_basic(1, 1.0, 1.0, (0, 0, 0), (0.0, 1.0, 0.0), (0.0, 1.0, 0.0))
+    with pytest.raises(native.RtError):
+        native.camera_make_basic(1, 1.0, 1.0, (0, 0, 0), (0.0, 2.0, 0.0), (0.0, 0.0, 1.0))
+
+
+def test_ppm_writer_matches_reference_golden_and_oracle():
+    # RayTracing.Test/PpmOutputExample.txt via TestPpmOutput.fs:12-46 (the Wikipedia P3 example)
+    px = np.array([[[255, 0, 0], [0, 255, 0], [0, 0, 255]], [[255, 255, 0], [255, 255, 255], [0, 0, 0]]], np.uint8)
+    golden = open(os.path.join(ROOT, "tests", "golden", "PpmOutputExample.txt"), "rb").read()
+    assert native.ppm_format(px, False) == golden
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, (37, 53, 3)).astype(np.uint8)
+    for gamma in (False, True):
+        assert native.ppm_format(img, gamma) == oracle.ppm_format(img, gamma)
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "o.ppm")
+        native.ppm_write_file(img, path, True)
+        assert open(path, "rb").read() == oracle.ppm_format(img, True)
+
+
+def test_gamma_correct_all_bytes():
+    for b in range(256):
+        assert native.gamma_correct(b) == oracle.gamma_correct(b)
+    assert native.gamma_correct(0) == 0 and native.gamma_correct(255) == 255 and native.gamma_correct(64) == 128
+
+
+def _host_scene(spec):
+    hs, ts, keep = marshal(spec.objects)
+    return hs, ts, native.SceneHandle(hs, ts, device=-1, keepalive=keep)
+
+
+@pytest.mark.parametrize("which", ["C1", "C2", "C4", "reduced"])
+def test_reference_tree_equals_oracle_tree(which):
+    spec = small_random_spheres() if which == "reduced" else sample_images.CONFIGS[which]()
+    hs, ts, h = _host_scene(spec)
+    b1, r1, p1 = h.bvh_nodes(abi.RT_BVH_REFERENCE)
+    b2, r2, p2 = oracle.Scene(hs, ts).bvh_nodes()
+    assert np.array_equal(r1, r2) and np.array_equal(p1, p2) and np.array_equal(b1, b2)
+    n_bounded = sum(1 for x in hs if x.shape == abi.RT_SHAPE_SPHERE)
+    assert len(r1) == max(0, 2 * n_bounded - 1)  # BoundingBoxTree: one object per leaf
+
+
+@pytest.mark.parametrize("which", ["C2", "C4", "reduced", "C5small"])
+def test_sah_tree_is_a_valid_bvh(which):
+    if which == "C5small":
+        spec = sample_images.many_spheres(n=3000)
+    else:
+        spec = small_random_spheres() if which == "reduced" else sample_images.CONFIGS[which]()
+    hs, ts, h = _host_scene(spec)
+    bounds, right, prim = h.bvh_nodes(abi.RT_BVH_SAH)
+    want = sorted(i for i, x in enumerate(hs) if x.shape == abi.RT_SHAPE_SPHERE and x.radius >= 0)  # F16: r < 0 is never hit
+    leaves = sorted(int(p) for p in prim if p >= 0)
+    assert leaves == want
+    # every node's box encloses its subtree (DFS pre-order: left child = i + 1)
+    def check(i):
+        if right[i] < 0:
+            x = hs[prim[i]]
+            # the device intersects the FP32-rounded sphere, so that is what the box must enclose
+            c, r = np.array(x.p, np.float32).astype(np.float64), float(np.float32(x.radius))
+            assert (bounds[i, :3] <= c - r).all() and (bounds[i, 3:] >= c + r).all()
+            return bounds[i, :3], bounds[i, 3:]
+        lmn, lmx = check(i + 1)
+        rmn, rmx = check(right[i])
+        assert (bounds[i, :3] <= np.minimum(lmn, rmn)).all() and (bounds[i, 3:] >= np.maximum(lmx, rmx)).all()
+        return bounds[i, :3], bounds[i, 3:]
+    import sys
+    sys.setrecursionlimit(10000)
+    if len(right):
+        check(0)
+
+
+def test_scene_create_validates_like_the_type_system_would():
+    lib = native.lib()
+
+    def create(hs, ts=()):
+        H = (abi.RtHittable * max(1, len(hs)))(*hs)
+        T = (abi.RtTexture * max(1, len(ts)))(*ts)
+        out = C.c_void_p()
+        rc = lib.rt_scene_create(H, len(hs), T, len(ts), -1, C.byref(out))
+        if rc == 0:
+            lib.rt_scene_destroy(out)
+        return rc, lib.rt_last_error().decode()
+
+    ok = abi.RtHittable()
+    ok.shape, ok.style, ok.radius, ok.texture = abi.RT_SHAPE_SPHERE, abi.RT_STYLE_GLASS, 1.0, -1
+    assert create([ok])[0] == abi.RT_OK
+    bad = abi.RtHittable.from_buffer_copy(ok)
+    bad.shape = 9
+    assert create([bad])[0] == abi.RT_ERR_INVALID_ARGUMENT
+    bad = abi.RtHittable.from_buffer_copy(ok)
+    bad.shape, bad.n[1] = abi.RT_SHAPE_INFINITE_PLANE, 1.0  # InfinitePlaneStyle has no Glass case (F13)
+    rc, msg = create([bad])
+    assert rc == abi.RT_ERR_INVALID_ARGUMENT and "InfinitePlaneStyle" in msg
+    bad = abi.RtHittable.from_buffer_copy(ok)
+    bad.texture = 3
+    assert create([bad])[0] == abi.RT_ERR_INVALID_ARGUMENT
+    bad = abi.RtHittable.from_buffer_copy(ok)
+    bad.p[0] = float("nan")
+    assert create([bad])[0] == abi.RT_ERR_INVALID_ARGUMENT
+    t = abi.RtTexture()
+    t.kind = 7
+    assert create([ok], [t])[0] == abi.RT_ERR_UNSUPPORTED
+    assert lib.rt_scene_create(None, 0, None, 0, -1, None) == abi.RT_ERR_INVALID_ARGUMENT
+
+
+def test_closures_cannot_cross_the_abi():
+    s = Hittable.Sphere(Sphere.make(SphereStyle.LambertReflection(1.0, Texture.Arbitrary(lambda p: Colour.Red)), (0, 0, 0), 1.0))
+    with pytest.raises(NotImplementedError):
+        marshal([s])
+
+
+def test_marshal_preserves_texture_structure():
+    interpret = Sphere.plane_map_inverse(2.0, (1.0, 2.0, 3.0))
+    img = np.arange(4 * 6 * 3, dtype=np.uint8).reshape(4, 6, 3)
+    tex = ParameterisedTexture.Checkered(ParameterisedTexture.of_image(img), ParameterisedTexture.Colour(Colour.Blue), 5.0)
+    objs = [Hittable.Sphere(Sphere.make(SphereStyle.LambertReflection(0.5, ParameterisedTexture.to_texture(interpret, tex)), (1, 2, 3), 2.0)),
+            Hittable.InfinitePlane(InfinitePlane.make(InfinitePlaneStyle.PureReflection(0.9, Pixel(1, 2, 3)), (0, 0, 0), (0, 1, 0)))]
+    hs, ts, keep = marshal(objs)
+    assert len(ts) == 3 and ts[hs[0].texture].kind == abi.RT_TEX_CHECKERED
+    chk = ts[hs[0].texture]
+    assert ts[chk.even].kind == abi.RT_TEX_IMAGE and ts[chk.odd].kind == abi.RT_TEX_COLOUR
+    assert (ts[chk.even].width, ts[chk.even].height) == (6, 4)
+    # ofImage flips rows (Texture.fs:34): img[0] is the bottom row of the bitmap
+    assert ts[chk.even].rgb8[0] == img[3, 0, 0]
+    assert list(chk.map_centre) == [1.0, 2.0, 3.0] and chk.map_radius == 2.0
+    assert hs[1].shape == abi.RT_SHAPE_INFINITE_PLANE and list(hs[1].colour) == [1, 2, 3] and hs[1].texture == -1
+
+
+def test_no_cpu_fallback_without_a_device():
+    if native.device_count() > 0:
+        pytest.skip("a GPU is present")
+    spec = sample_images.few_spheres()
+    hs, ts, keep = marshal(spec.objects)
+    with pytest.raises(native.RtError) as e:
+        native.SceneHandle(hs, ts, 0, keepalive=keep)
+    assert e.value.code == abi.RT_ERR_NO_DEVICE
+    h = native.SceneHandle(hs, ts, -1, keepalive=keep)  # host-only handle: inspection works, compute does not
+    cam = native.camera_make_basic(4, 1.0, 1.0, (0, 0, 0), (0.0, 0.0, 1.0), (0.0, 1.0, 0.0))
+    with pytest.raises(native.RtError) as e:
+        h.render(cam, 4, 4)
+    assert e.value.code == abi.RT_ERR_NO_DEVICE
+    with pytest.raises(native.RtError) as e:
+        native.sphere_hit([0, 0, 0], [0, 0, 1], [0, 0, 5], [1.0])
+    assert e.value.code == abi.RT_ERR_NO_DEVICE
+    with pytest.raises(native.RtError) as e:
+        native.MultiHandle(hs, ts, [0, 1])
+    assert e.value.code == abi.RT_ERR_NO_DEVICE
+
+
+def test_product_package_never_touches_the_oracle():
+    pkg = os.path.join(ROOT, "ray_tracing_fsharp_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if "build" in dirpath.split(os.sep):
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert not re.search(r"^\s*(import|from)\s+oracle\b", text, flags=re.M), f
+                assert "liboracle" not in text and "oracle.cpp" not in text, f
+    # and the shared library does not link it
+    out = subprocess.check_output(["ldd", native.LIB_PATH], text=True)
+    assert "oracle" not in out
