@@ -283,6 +283,15 @@ def run_ours(args):
         e2e_secs += float(dt.item())
         e2e_rays += int(rr.item())
 
+    # one extra, untimed frame with the traversal counters on (a slower kernel variant): tests per ray of OUR traversal
+    traversal = None
+    if args.counters:
+        be = DeviceBackend(scene, cam, max_w, max_h, seed=4000, adaptive=adaptive, flags=flags | abi.RT_FLAG_COUNTERS)
+        render_split_frame(be, rank, world, red_max, red_sum)
+        c = be.counters()
+        traversal = {"box_tests_per_ray": c.box_tests / max(1, c.rays), "prim_tests_per_ray": c.prim_tests / max(1, c.rays),
+                     "rays_per_path": c.rays / max(1, c.paths)}
+
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -321,6 +330,8 @@ def run_ours(args):
                          "note": "achieved = rays/s x FLOPs the REFERENCE traversal spends per ray (exhaustive DFS, SURVEY §8d); peak = FP32 FMA "
                                  "microbenchmark measured in this run (MEASURED_PEAKS.json has no FP32 figure)"},
         }
+        if traversal:
+            line["traversal"] = traversal
         if cpu:
             line["cpu_baseline"] = {k: v for k, v in cpu.items() if k != "counters"}
         print(json.dumps(line), flush=True)
@@ -341,6 +352,7 @@ def main():
     ap.add_argument("--no-adaptive", action="store_true")
     ap.add_argument("--no-smem", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--counters", action="store_true", help="also report box / primitive tests per ray of the device traversal")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--flops-per-ray", type=float, default=0.0)
     args = ap.parse_args()

@@ -230,17 +230,16 @@ RTFS_HD bool sphere_hit(float3 o, float3 d, float4 s, bool self, float &t_out) {
 }
 // FP64 form for unbounded spheres (o, d are the FP32 ray promoted exactly).  d is unit only to ~1e-7, so
 // the quadratic keeps its leading coefficient a = d.d: the strike point then lies on the sphere to FP64
-// accuracy, as it does in the reference.
-RTFS_HD bool sphere_hit_f64(D3 o, D3 d, const DUnbounded &s, bool self, double &t_out) {
+// accuracy, as it does in the reference.  inv_a = 1 / (d.d), computed once per ray.
+RTFS_HD bool sphere_hit_f64(D3 o, D3 d, double inv_a, const DUnbounded &s, bool self, double &t_out) {
     D3 oc = o - D3{s.p[0], s.p[1], s.p[2]};
-    double a = dot(d, d);
-    double b = dot(d, oc) / a;
+    double b = dot(d, oc) * inv_a;
     if (self) {
         double t = -2.0 * b;
         t_out = t;
         return t > kTolD;
     }
-    double c = (dot(oc, oc) - s.r2) / a;
+    double c = (dot(oc, oc) - s.r2) * inv_a;
     double disc = b * b - c;
     double ip;
     if (fabs(disc) < kTolD) {
@@ -384,6 +383,7 @@ RTFS_HD Hit closest_hit(const SceneAccess<SMEM> &sc, float3 o, float3 d, int las
     h.strike = fma3(best_t, d, o);
     if (sc.g.n_unbounded > 0) {
         D3 od = d3(o), dd = d3(d);
+        const double inv_a = 1.0 / dot(dd, dd);
         double best_a = double(best_t) * double(best_t);
         double best_td = 0.0;
         int best_u = kNoPrim;
@@ -391,7 +391,7 @@ RTFS_HD Hit closest_hit(const SceneAccess<SMEM> &sc, float3 o, float3 d, int las
             const DUnbounded &u = sc.g.unb[i];
             double t;
             bool self = (sc.g.n_bounded + i) == last;
-            bool hit = (u.shape == RT_SHAPE_INFINITE_PLANE) ? plane_hit_f64(od, dd, u, self, t) : sphere_hit_f64(od, dd, u, self, t);
+            bool hit = (u.shape == RT_SHAPE_INFINITE_PLANE) ? plane_hit_f64(od, dd, u, self, t) : sphere_hit_f64(od, dd, inv_a, u, self, t);
             if (COUNT) cn.prim_tests += 1;
             if (hit) {
                 double a = t * t;
@@ -449,12 +449,13 @@ RTFS_HD Hit closest_hit_reference(const DRefNode *ref_nodes, int n_ref_nodes, co
     Hit h;
     h.strike = fma3(best_t, d, o);
     D3 od = d3(o), dd = d3(d);
+    const double inv_a = 1.0 / dot(dd, dd);
     double best_a = double(best_t) * double(best_t);
     for (int i = 0; i < g.n_unbounded; ++i) {
         const DUnbounded &u = g.unb[i];
         double t;
         bool self = (g.n_bounded + i) == last;
-        bool hit = (u.shape == RT_SHAPE_INFINITE_PLANE) ? plane_hit_f64(od, dd, u, self, t) : sphere_hit_f64(od, dd, u, self, t);
+        bool hit = (u.shape == RT_SHAPE_INFINITE_PLANE) ? plane_hit_f64(od, dd, u, self, t) : sphere_hit_f64(od, dd, inv_a, u, self, t);
         if (hit && fcmp(t * t, best_a) == CMP_LESS) {
             best_a = t * t;
             best = g.n_bounded + i;

@@ -249,37 +249,45 @@ __global__ void __launch_bounds__(kBlockThreads) render_kernel(const FrameParams
         }
         ws->acc[0][0][lane] = 0; ws->acc[0][1][lane] = 0; ws->acc[0][2][lane] = 0;
         if (PROBE) { ws->acc[1][0][lane] = 0; ws->acc[1][1][lane] = 0; ws->acc[1][2][lane] = 0; }
-        ws->pix[lane] = my_pixel;
+        ws->pix[lane] = my_pixel < 0 ? -1 : (((my_pixel / fp.cam.cols) << 16) | (my_pixel % fp.cam.cols));
         if (lane == 0) ws->cursor = 0;
         __syncwarp();
         const int pool = n_entries * j_len;
 
         // ---- drain the pool ----
+        // No lane leaves this loop before the whole warp is done: the full-mask vote below is the point where the
+        // warp reconverges every iteration (lanes that regenerate a path and lanes that do not would otherwise drift
+        // apart for good, and the traversal would run at a fraction of the warp width).
         PathState ps;
-        bool active = false;
+        bool active = false, dry = false;
         int slot = 0, set = 0;
         for (;;) {
-            if (!active) {
+            if (!active && !dry) {
                 int q = atomicAdd(&ws->cursor, 1);
-                if (q >= pool) break;
-                int j = q / n_entries;
-                slot = q - j * n_entries;
-                int pixel = ws->pix[slot];
-                if (pixel < 0) continue; // the tile overhangs the image edge: nothing to trace for this slot
-                uint32_t sample = uint32_t(PROBE ? j : fp.sample_begin + fp.rank + (j_begin + j) * fp.world);
-                set = (PROBE && j > fp.first_trial) ? 1 : 0;
-                int r = pixel / fp.cam.cols, c = pixel - r * fp.cam.cols;
-                ++n_paths;
-                if (!path_begin(ps, fp.cam, fp.k0, fp.k1, r, c, sample)) continue; // Ray.make' failed: the reference throws
-                active = true;
+                if (q >= pool) {
+                    dry = true;
+                } else {
+                    int j = q / n_entries;
+                    slot = q - j * n_entries;
+                    int rc = ws->pix[slot]; // row << 16 | col, or -1 where the tile overhangs the image edge
+                    if (rc >= 0) {
+                        uint32_t sample = uint32_t(PROBE ? j : fp.sample_begin + fp.rank + (j_begin + j) * fp.world);
+                        set = (PROBE && j > fp.first_trial) ? 1 : 0;
+                        ++n_paths;
+                        active = path_begin(ps, fp.cam, fp.k0, fp.k1, rc >> 16, rc & 0xffff, sample); // false: Ray.make' failed (the reference throws)
+                    }
+                }
             }
-            uint32_t result;
-            ++n_rays;
-            if (path_step<SMEM, COUNT>(ps, sc, fp.cam.depth, result, cn)) {
-                atomicAdd(&ws->acc[set][0][slot], int((result >> 16) & 255u));
-                atomicAdd(&ws->acc[set][1][slot], int((result >> 8) & 255u));
-                atomicAdd(&ws->acc[set][2][slot], int(result & 255u));
-                active = false;
+            if (!__any_sync(0xffffffffu, active || !dry)) break;
+            if (active) {
+                uint32_t result;
+                ++n_rays;
+                if (path_step<SMEM, COUNT>(ps, sc, fp.cam.depth, result, cn)) {
+                    atomicAdd(&ws->acc[set][0][slot], int((result >> 16) & 255u));
+                    atomicAdd(&ws->acc[set][1][slot], int((result >> 8) & 255u));
+                    atomicAdd(&ws->acc[set][2][slot], int(result & 255u));
+                    active = false;
+                }
             }
         }
         __syncwarp();
@@ -355,7 +363,7 @@ int check_frame_args(const RtScene *scene, const RtCamera *camera, int max_w, in
     if (!scene || !camera || !opts) return fail(RT_ERR_INVALID_ARGUMENT, "render: null argument");
     if (!scene->dev) return fail(RT_ERR_NO_DEVICE, "render: the scene was created without a device (device = -1); there is no CPU fallback");
     if (max_w <= 0 || max_h <= 0) return fail(RT_ERR_INVALID_ARGUMENT, "render: maxWidthCoord and maxHeightCoord must be positive");
-    if (size_t(2 * max_w + 1) * size_t(2 * max_h + 1) > (size_t(1) << 30)) return fail(RT_ERR_INVALID_ARGUMENT, "render: image too large");
+    if (max_w > 32767 || max_h > 16383) return fail(RT_ERR_INVALID_ARGUMENT, "render: image too large (at most 65535 x 32767)");
     if (camera->samples_per_pixel < 1 || camera->samples_per_pixel > (1 << 22))
         return fail(RT_ERR_INVALID_ARGUMENT, "render: samples_per_pixel must be in [1, 2^22] (integer sums are 32-bit)");
     if (camera->bounce_depth < 0) return fail(RT_ERR_INVALID_ARGUMENT, "render: bounce_depth must be non-negative");

@@ -62,8 +62,10 @@ def small_random_spheres(n_side=4, seed=3):
 
 
 def camera_sample_rays(spec, cam, rng, n):
-    """Primary rays of random pixels (FP32-representable), as the oracle generates them."""
+    """Primary rays of random pixels as the oracle generates them: FP32-representable origins, unit directions in
+    double (the oracle's formulas assume |d| = 1 to double precision, as the reference's UnitVector guarantees; the
+    device receives the same direction rounded to FP32)."""
     row = rng.integers(-spec.max_height_coord - 1, spec.max_height_coord, n).astype(np.int32)
     col = rng.integers(-spec.max_width_coord, spec.max_width_coord + 1, n).astype(np.int32)
     o, d = oracle.camera_rays(cam, spec.max_width_coord, spec.max_height_coord, row, col, rng.random(n), rng.random(n))
-    return f32(o), f32(d)
+    return f32(o), d
