@@ -37,8 +37,12 @@ for r in rows[start + 1:]:
         body.append(r)
 assert len(body) == len(loc), (len(body), len(loc))
 
-REGIONS = [  # rtfs_core.cuh line ranges -> label (kept in sync by hand; see the function headers there)
-]
+REGIONS = []  # optional: file with "first last label" lines for rtfs_core.cuh, argv[6]
+if len(sys.argv) > 6:
+    for l in open(sys.argv[6]):
+        if l.strip() and not l.startswith("#"):
+            a, b, label = l.split(None, 2)
+            REGIONS.append((int(a), int(b), label.strip()))
 per_line = defaultdict(lambda: [0, 0, 0])
 for (fl, sass), r in zip(loc, body):
     a, t, s = int(r[ia]), int(r[it]), int(r[ist] or 0)
@@ -53,3 +57,20 @@ print(f"total warp-instr {tot_a:.4g}  thread-instr {tot_t:.4g}  avg active {tot_
 print(f"{'file:line':34s} {'warp-instr %':>12s} {'avg lanes':>9s} {'samples %':>9s}")
 for fl, v in sorted(per_line.items(), key=lambda x: -x[1][0])[:int(sys.argv[5]) if len(sys.argv) > 5 else 60]:
     print(f"{fl[0] + ':' + str(fl[1]):34s} {100 * v[0] / tot_a:12.2f} {v[1] / max(1, v[0]):9.2f} {100 * v[2] / max(1, tot_s):9.2f}")
+
+if REGIONS:
+    reg = defaultdict(lambda: [0, 0, 0])
+    for fl, v in per_line.items():
+        label = "other (" + fl[0] + ")"
+        if fl[0] == "rtfs_core.cuh":
+            for a, b, lab in REGIONS:
+                if a <= fl[1] <= b:
+                    label = lab
+                    break
+        e = reg[label]
+        for k in range(3):
+            e[k] += v[k]
+    print()
+    print(f"{'region':44s} {'warp-instr %':>12s} {'thread-instr %':>14s} {'avg lanes':>9s} {'samples %':>9s}")
+    for lab, v in sorted(reg.items(), key=lambda x: -x[1][0]):
+        print(f"{lab:44s} {100 * v[0] / tot_a:12.2f} {100 * v[1] / tot_t:14.2f} {v[1] / max(1, v[0]):9.2f} {100 * v[2] / max(1, tot_s):9.2f}")

@@ -66,16 +66,16 @@ __global__ void k_sphere_hit(int n, const float *o, const float *d, const float 
     bool hit = sphere_hit(ld3(o, i), ld3(d, i), make_float4(cc.x, cc.y, cc.z, r[i]), false, t);
     t_out[i] = hit ? t : CUDART_NAN_F;
 }
-__global__ void k_plane_hit(int n, const float *o, const float *d, const double *p, const float *nrm, double *t_out) {
+__global__ void k_plane_hit(int n, const float *o, const float *d, const double *p, const float *nrm, float *t_out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     DUnbounded u;
     u.p[0] = p[3 * i]; u.p[1] = p[3 * i + 1]; u.p[2] = p[3 * i + 2];
     u.n[0] = nrm[3 * i]; u.n[1] = nrm[3 * i + 1]; u.n[2] = nrm[3 * i + 2];
     u.shape = RT_SHAPE_INFINITE_PLANE;
-    double t;
-    bool hit = plane_hit_f64(d3(ld3(o, i)), d3(ld3(d, i)), u, false, t);
-    t_out[i] = hit ? t : CUDART_NAN;
+    float t;
+    bool hit = plane_hit_big(d3(ld3(o, i)), d3(ld3(d, i)), u, false, t);
+    t_out[i] = hit ? t : CUDART_NAN_F;
 }
 __global__ void k_aabb_hit(int n, const float *o, const float *d, const float *mn, const float *mx, uint8_t *out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -257,8 +257,8 @@ int rt_test_plane_hit(int32_t device, int32_t n, const double *origin, const dou
                       double *t_out) {
     RT_TRY(require_device(device));
     if (n < 0 || !origin || !dir || !point || !normal || !t_out) return fail(RT_ERR_INVALID_ARGUMENT, "rt_test_plane_hit: bad argument");
-    DevBuf<float> o, d, nr;
-    DevBuf<double> p, t;
+    DevBuf<float> o, d, nr, t;
+    DevBuf<double> p;
     RT_TRY(o.put(to_f32(origin, 3 * size_t(n))));
     RT_TRY(d.put(to_f32(dir, 3 * size_t(n))));
     RT_TRY(nr.put(to_f32(normal, 3 * size_t(n))));
@@ -266,9 +266,9 @@ int rt_test_plane_hit(int32_t device, int32_t n, const double *origin, const dou
     RT_TRY(t.alloc(n));
     if (n) k_plane_hit<<<grid_for(n), 128>>>(n, o.p, d.p, p.p, nr.p, t.p);
     RT_TRY(finish_launch());
-    std::vector<double> h;
+    std::vector<float> h;
     RT_TRY(t.get(h));
-    for (int i = 0; i < n; ++i) t_out[i] = h[i];
+    for (int i = 0; i < n; ++i) t_out[i] = double(h[i]);
     return RT_OK;
 }
 

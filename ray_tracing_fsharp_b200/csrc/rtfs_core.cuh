@@ -168,29 +168,36 @@ RTFS_HD bool aabb_hits_ref(float3 inv, float3 o, const float mn[3], const float 
 }
 RTFS_HD float3 inverse_directions(float3 d) { return f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z); }
 
-// Slab test of the render traversal: conservative (boxes are rounded outwards on the host, tMax is
-// padded by 2 ulp as in Ize, "Robust BVH Ray Traversal"), returns the entry distance for ordering and
-// culls against the best hit so far (a finite number: kNoHitT while nothing is hit, so that the empty box
-// {+inf, +inf} of a one-leaf tree is never entered).  It may accept a box the reference rejects or vice versa only for
-// rays within rounding of a box face; closest-hit results do not depend on it (checked by
-// rt_test_hit_object(traversal = 0) against the oracle).
-RTFS_HD bool slab_entry(float3 inv, float3 o, float mnx, float mny, float mnz, float mxx, float mxy, float mxz, float best_t,
-                        float &entry) {
-    float ax = (mnx - o.x) * inv.x, bx = (mxx - o.x) * inv.x;
-    float ay = (mny - o.y) * inv.y, by = (mxy - o.y) * inv.y;
-    float az = (mnz - o.z) * inv.z, bz = (mxz - o.z) * inv.z;
-    float t_near = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
-    float t_far = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)) * 1.0000003576278687f;
-    entry = t_near;
-    return t_near <= fminf(t_far, best_t);
-}
-// direction components are clamped away from zero so that inv stays finite (no 0 * inf = NaN in the slabs)
-RTFS_HD float3 safe_inverse(float3 d) {
+// Slab test of the render traversal.  Per ray: inv = 1 / d (components clamped away from zero, so no
+// 0 * inf = NaN arises), noi = -o * inv, and pad = an absolute bound on the rounding of mn * inv + noi; per box:
+// six FFMAs.  Conservative: boxes are rounded outwards on the host, t_far is padded by 3 ulp (Ize, "Robust BVH
+// Ray Traversal") plus `pad`.  Returns the entry distance for ordering and culls against the best hit so far
+// (a finite number: kNoHitT while nothing is hit, so that the box {+inf, +inf} of a one-leaf tree is never
+// entered).  It may accept a box the reference rejects only for rays within rounding of a box face; closest-hit
+// results do not depend on it (rt_test_hit_object(traversal = 0) checks them against the oracle).
+struct RaySlabs {
+    float3 inv, noi;
+    float pad;
+};
+RTFS_HD RaySlabs make_slabs(float3 o, float3 d) {
     const float tiny = 1e-30f;
     float x = fabsf(d.x) < tiny ? copysignf(tiny, d.x) : d.x;
     float y = fabsf(d.y) < tiny ? copysignf(tiny, d.y) : d.y;
     float z = fabsf(d.z) < tiny ? copysignf(tiny, d.z) : d.z;
-    return f3(1.0f / x, 1.0f / y, 1.0f / z);
+    RaySlabs r;
+    r.inv = f3(1.0f / x, 1.0f / y, 1.0f / z);
+    r.noi = f3(-o.x * r.inv.x, -o.y * r.inv.y, -o.z * r.inv.z);
+    r.pad = 4.8e-7f * fmaxf(fmaxf(fabsf(r.noi.x), fabsf(r.noi.y)), fabsf(r.noi.z));
+    return r;
+}
+RTFS_HD bool slab_entry(const RaySlabs &r, float mnx, float mny, float mnz, float mxx, float mxy, float mxz, float best_t, float &entry) {
+    float ax = fmaf(mnx, r.inv.x, r.noi.x), bx = fmaf(mxx, r.inv.x, r.noi.x);
+    float ay = fmaf(mny, r.inv.y, r.noi.y), by = fmaf(mxy, r.inv.y, r.noi.y);
+    float az = fmaf(mnz, r.inv.z, r.noi.z), bz = fmaf(mxz, r.inv.z, r.noi.z);
+    float t_near = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
+    float t_far = fmaf(fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)), 1.0000003576278687f, r.pad);
+    entry = t_near;
+    return t_near <= fminf(t_far, best_t);
 }
 
 // ---- Sphere.firstIntersection (Sphere.fs:349-386) -------------------------------------------------------
@@ -228,30 +235,41 @@ RTFS_HD bool sphere_hit(float3 o, float3 d, float4 s, bool self, float &t_out) {
     t_out = ip;
     return ip > kTolF;
 }
-// FP64 form for unbounded spheres (o, d are the FP32 ray promoted exactly).  d is unit only to ~1e-7, so
-// the quadratic keeps its leading coefficient a = d.d: the strike point then lies on the sphere to FP64
-// accuracy, as it does in the reference.  inv_a = 1 / (d.d), computed once per ray.
-RTFS_HD bool sphere_hit_f64(D3 o, D3 d, double inv_a, const DUnbounded &s, bool self, double &t_out) {
+// Unbounded spheres (typically huge: the r = 1000 floor, the r = 2000 light dome).  |o - c|^2 - r^2 and
+// b^2 - c cancel catastrophically in FP32, so exactly those terms are evaluated in FP64 (on the FP32 ray promoted
+// exactly); the square root and the roots are FP32, each root in its cancellation-free form (the product of the
+// roots is c / a).  d is unit only to ~1e-7, so the quadratic keeps its leading coefficient a = d.d.
+// Root selection follows Sphere.firstIntersection (Sphere.fs:349-386) line by line.
+RTFS_HD bool sphere_hit_big(D3 o, D3 d, double a, const DUnbounded &s, bool self, float &t_out) {
     D3 oc = o - D3{s.p[0], s.p[1], s.p[2]};
-    double b = dot(d, oc) * inv_a;
-    if (self) {
-        double t = -2.0 * b;
+    double b = dot(d, oc);
+    float inv_a = 1.0f / float(a);
+    if (self) { // c = 0: roots 0 and -2b / a; the reference keeps the one that is `positive`
+        float t = -2.0f * float(b) * inv_a;
         t_out = t;
-        return t > kTolD;
+        return t > kTolF;
     }
-    double c = (dot(oc, oc) - s.r2) * inv_a;
-    double disc = b * b - c;
-    double ip;
-    if (fabs(disc) < kTolD) {
-        ip = -b;
-    } else if (disc < 0.0) {
+    double c = dot(oc, oc) - s.r2;
+    float disc = float(b * b - a * c), bf = float(b), cf = float(c);
+    float ip;
+    if (fabsf(disc) < kTolF) { // Float.compare disc 0 = Equal
+        ip = -bf * inv_a;
+    } else if (disc < 0.0f) {
         return false;
     } else {
-        double im = sqrt(disc);
-        double i1 = im - b, i2 = -(b + im);
-        bool p1 = i1 > kTolD, p2 = i2 > kTolD;
+        float im = sqrtf(disc);
+        float q1 = im - bf, q2 = -(bf + im); // i1 = q1 / a (the larger root), i2 = q2 / a; q1 * q2 = a * c
+        float i1, i2;
+        if (bf < 0.0f) {
+            i1 = q1 * inv_a;
+            i2 = cf / q1;
+        } else {
+            i2 = q2 * inv_a;
+            i1 = (q2 != 0.0f) ? cf / q2 : 0.0f;
+        }
+        bool p1 = i1 > kTolF, p2 = i2 > kTolF;
         if (p1 && p2)
-            ip = (fabs(i1 - i2) < kTolD || i1 < i2) ? i1 : i2;
+            ip = (fabsf(i1 - i2) < kTolF || i1 < i2) ? i1 : i2;
         else if (p1)
             ip = i1;
         else if (p2)
@@ -260,27 +278,18 @@ RTFS_HD bool sphere_hit_f64(D3 o, D3 d, double inv_a, const DUnbounded &s, bool 
             return false;
     }
     t_out = ip;
-    return ip > kTolD;
+    return ip > kTolF;
 }
-// InfinitePlane.intersection (InfinitePlane.fs:125-136), FP64 on the promoted FP32 ray
-RTFS_HD bool plane_hit_f64(D3 o, D3 d, const DUnbounded &p, bool self, double &t_out) {
-    if (self) return false; // numerator is 0 on the plane: t = 0 is never `positive`
+// InfinitePlane.intersection (InfinitePlane.fs:125-136): numerator and denominator in FP64, quotient in FP32
+RTFS_HD bool plane_hit_big(D3 o, D3 d, const DUnbounded &p, bool self, float &t_out) {
+    if (self) return false; // the numerator is 0 on the plane: t = 0 is never `positive`
     D3 n{double(p.n[0]), double(p.n[1]), double(p.n[2])};
-    double den = dot(n, d);
-    if (fabs(den) < kTolD) return false;
-    double t = dot(n, D3{p.p[0], p.p[1], p.p[2]} - o) / den;
-    t_out = t;
-    return t > kTolD;
-}
-// FP32 forms used by the per-primitive conformance entry points on arbitrary (non-self) inputs
-RTFS_HD bool plane_hit(float3 o, float3 d, float3 p, float3 n, float &t_out) {
-    float den = dot(n, d);
+    float den = float(dot(n, d));
     if (fabsf(den) < kTolF) return false;
-    float t = dot(n, p - o) / den;
+    float t = float(dot(n, D3{p.p[0], p.p[1], p.p[2]} - o)) / den;
     t_out = t;
     return t > kTolF;
 }
-
 // ---- scene access ------------------------------------------------------------------------------------
 // The render kernels read the flattened BVH either from global memory through the read-only path
 // (128-bit __ldg) or from a copy staged in shared memory (128-bit LDS); the template parameter picks.
@@ -295,22 +304,28 @@ struct SceneGlobal {
 
 #ifdef __CUDACC__
 extern __shared__ uint4 rtfs_smem[];
+// 128-bit load from a 32-bit shared-window address (one LDS.128, no generic-address arithmetic)
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
 #endif
 
 template <bool SMEM>
 struct SceneAccess {
     SceneGlobal g;
-    uint32_t s_nodes, s_spheres, s_mats; // offsets into rtfs_smem in uint4 units (SMEM only)
+    uint32_t s_nodes, s_spheres, s_mats; // SMEM only: byte addresses of the staged copies in the shared window
     RTFS_HD uint4 node_q(int i, int q) const {
 #ifdef __CUDACC__
-        if (SMEM) return rtfs_smem[s_nodes + 4u * uint32_t(i) + uint32_t(q)];
+        if (SMEM) return lds128(s_nodes + 64u * uint32_t(i) + 16u * uint32_t(q));
 #endif
         return __ldg(g.nodes + 4 * i + q);
     }
     RTFS_HD float4 sphere(int i) const {
 #ifdef __CUDACC__
         if (SMEM) {
-            uint4 v = rtfs_smem[s_spheres + uint32_t(i)];
+            uint4 v = lds128(s_spheres + 16u * uint32_t(i));
             return make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
         }
 #endif
@@ -318,7 +333,7 @@ struct SceneAccess {
     }
     RTFS_HD uint4 mat_q(int i, int q) const {
 #ifdef __CUDACC__
-        if (SMEM) return rtfs_smem[s_mats + 2u * uint32_t(i) + uint32_t(q)];
+        if (SMEM) return lds128(s_mats + 32u * uint32_t(i) + 16u * uint32_t(q));
 #endif
         return __ldg(g.mats + 2 * i + q);
     }
@@ -343,7 +358,7 @@ RTFS_HD Hit closest_hit(const SceneAccess<SMEM> &sc, float3 o, float3 d, int las
     float best_t = kNoHitT;
     int best = kNoPrim;
     if (sc.g.n_bounded > 0) {
-        float3 inv = safe_inverse(d);
+        const RaySlabs rs = make_slabs(o, d);
         int stack[64];
         int sp = 0;
         int node = 0;
@@ -351,9 +366,9 @@ RTFS_HD Hit closest_hit(const SceneAccess<SMEM> &sc, float3 o, float3 d, int las
             if (node >= 0) {
                 uint4 q0 = sc.node_q(node, 0), q1 = sc.node_q(node, 1), q2 = sc.node_q(node, 2), q3 = sc.node_q(node, 3);
                 float tl, tr;
-                bool hl = slab_entry(inv, o, __uint_as_float(q0.x), __uint_as_float(q0.y), __uint_as_float(q0.z),
+                bool hl = slab_entry(rs, __uint_as_float(q0.x), __uint_as_float(q0.y), __uint_as_float(q0.z),
                                      __uint_as_float(q0.w), __uint_as_float(q1.x), __uint_as_float(q1.y), best_t, tl);
-                bool hr = slab_entry(inv, o, __uint_as_float(q1.z), __uint_as_float(q1.w), __uint_as_float(q2.x),
+                bool hr = slab_entry(rs, __uint_as_float(q1.z), __uint_as_float(q1.w), __uint_as_float(q2.x),
                                      __uint_as_float(q2.y), __uint_as_float(q2.z), __uint_as_float(q2.w), best_t, tr);
                 if (COUNT) cn.box_tests += 2;
                 int left = int(q3.x), right = int(q3.y);
@@ -379,37 +394,26 @@ RTFS_HD Hit closest_hit(const SceneAccess<SMEM> &sc, float3 o, float3 d, int las
             node = stack[--sp];
         }
     }
-    Hit h;
-    h.strike = fma3(best_t, d, o);
     if (sc.g.n_unbounded > 0) {
-        D3 od = d3(o), dd = d3(d);
-        const double inv_a = 1.0 / dot(dd, dd);
-        double best_a = double(best_t) * double(best_t);
-        double best_td = 0.0;
-        int best_u = kNoPrim;
+        const D3 od = d3(o), dd = d3(d);
+        const double a = dot(dd, dd);
         for (int i = 0; i < sc.g.n_unbounded; ++i) {
             const DUnbounded &u = sc.g.unb[i];
-            double t;
+            float t;
             bool self = (sc.g.n_bounded + i) == last;
-            bool hit = (u.shape == RT_SHAPE_INFINITE_PLANE) ? plane_hit_f64(od, dd, u, self, t) : sphere_hit_f64(od, dd, inv_a, u, self, t);
+            bool hit = (u.shape == RT_SHAPE_INFINITE_PLANE) ? plane_hit_big(od, dd, u, self, t) : sphere_hit_big(od, dd, a, u, self, t);
             if (COUNT) cn.prim_tests += 1;
-            if (hit) {
-                double a = t * t;
-                if (fcmp(a, best_a) == CMP_LESS) {
-                    best_a = a;
-                    best_td = t;
-                    best_u = sc.g.n_bounded + i;
-                }
+            // Float.compare (t * t) bestFloat = Less, Scene.fs:82
+            if (hit && fcmp(t * t, best_t * best_t) == CMP_LESS) {
+                best_t = t;
+                best = sc.g.n_bounded + i;
             }
         }
-        if (best_u != kNoPrim) {
-            best = best_u;
-            best_t = float(best_td);
-            h.strike = f3(float(od.x + best_td * dd.x), float(od.y + best_td * dd.y), float(od.z + best_td * dd.z));
-        }
     }
+    Hit h;
     h.t = best_t;
     h.prim = best;
+    h.strike = fma3(best_t, d, o); // Ray.walkAlong ray bestLength, Scene.fs:91
     return h;
 }
 
@@ -446,25 +450,23 @@ RTFS_HD Hit closest_hit_reference(const DRefNode *ref_nodes, int n_ref_nodes, co
             node = stack[--sp];
         }
     }
-    Hit h;
-    h.strike = fma3(best_t, d, o);
-    D3 od = d3(o), dd = d3(d);
-    const double inv_a = 1.0 / dot(dd, dd);
-    double best_a = double(best_t) * double(best_t);
+    const D3 od = d3(o), dd = d3(d);
+    const double a = dot(dd, dd);
+    if (best == kNoPrim) best_t = kNoHitT;
     for (int i = 0; i < g.n_unbounded; ++i) {
         const DUnbounded &u = g.unb[i];
-        double t;
+        float t;
         bool self = (g.n_bounded + i) == last;
-        bool hit = (u.shape == RT_SHAPE_INFINITE_PLANE) ? plane_hit_f64(od, dd, u, self, t) : sphere_hit_f64(od, dd, inv_a, u, self, t);
-        if (hit && fcmp(t * t, best_a) == CMP_LESS) {
-            best_a = t * t;
+        bool hit = (u.shape == RT_SHAPE_INFINITE_PLANE) ? plane_hit_big(od, dd, u, self, t) : sphere_hit_big(od, dd, a, u, self, t);
+        if (hit && fcmp(t * t, best_t * best_t) == CMP_LESS) {
+            best_t = t;
             best = g.n_bounded + i;
-            best_t = float(t);
-            h.strike = f3(float(od.x + t * dd.x), float(od.y + t * dd.y), float(od.z + t * dd.z));
         }
     }
+    Hit h;
     h.t = best_t;
     h.prim = best;
+    h.strike = fma3(best_t, d, o);
     return h;
 }
 
@@ -524,25 +526,22 @@ RTFS_HD Material load_material(const SceneAccess<SMEM> &sc, int prim) {
 // Sphere.reflectWithoutFuzz (Sphere.fs:68-87) / InfinitePlane.pureOutgoing (InfinitePlane.fs:18-38).
 // With T = unit(d - (n.d) n) the reference's -(n.d) n + (T.d) T equals d - 2 (n.d) n; when the tangent
 // cannot be normalised (|d - (n.d) n|^2 < 1e-8: the ray runs along the normal) it flips the ray.
-RTFS_HD float3 reflect_dir(float3 n, float3 d) {
-    float nd = dot(n, d);
-    float3 tangent = fma3(-nd, n, d);
+// `tangent` = d - (n.d) n is shared with refract_dir.
+RTFS_HD float3 reflect_dir(float3 n, float3 d, float nd, float3 tangent) {
     if (fabsf(dot(tangent, tangent)) < kTolF) return -d;
     float3 r = fma3(-nd, n, tangent);
     float3 out;
     if (!unitise(r, out)) return -d; // unreachable: |r| = 1
     return out;
 }
-// Sphere.refract (Sphere.fs:108-146)
-RTFS_HD float3 refract_dir(bool inside, float3 n, float3 d, float incoming_cos, float ior) {
+// Sphere.refract (Sphere.fs:108-146); `refl` is what reflectWithoutFuzz gives (total internal reflection)
+RTFS_HD float3 refract_dir(bool inside, float3 n, float3 d, float3 tangent, float3 refl, float incoming_cos, float ior) {
     float index = inside ? 1.0f / ior : ior;
-    float nd = dot(n, d);
-    float3 tangent = fma3(-nd, n, d);
     float3 tu;
     if (!unitise(tangent, tu)) return d; // parallel to the normal: straight through
     float incoming_sin = sqrtf(fmaxf(0.0f, 1.0f - incoming_cos * incoming_cos));
     float outgoing_sin = incoming_sin / index;
-    if (fcmp(outgoing_sin, 1.0f) == CMP_GREATER) return reflect_dir(n, d);
+    if (fcmp(outgoing_sin, 1.0f) == CMP_GREATER) return refl;
     float outgoing_cos = sqrtf(fmaxf(0.0f, 1.0f - outgoing_sin * outgoing_sin));
     float3 v = fma3(outgoing_sin, tu, (-outgoing_cos) * n);
     float3 out;
@@ -555,143 +554,111 @@ enum ScatterResult { SCATTER_CONTINUE = 0, SCATTER_ABSORBED = 1, SCATTER_ERROR =
 // Hittable.Reflection (Hittable.fs:8-12) -> Sphere.reflection (Sphere.fs:150-300) /
 // InfinitePlane.reflection (InfinitePlane.fs:43-99).  On SCATTER_CONTINUE the ray (o, d) and the colour
 // are updated in place; on SCATTER_ABSORBED `colour` is the emitted result.
+//
+// Written so that a warp whose lanes hit different materials shares as much as possible: one normal /
+// inside computation, one colour update, ONE block of the counter RNG for whichever style draws
+// (Lambert and Fuzzed: GetThree; Dielectric and Glass: Get — always the first block of the bounce), one
+// reflection, and a common "unit(base + scale * offset)" tail; only the few style-specific lines diverge.
 template <bool SMEM, class Rng>
 RTFS_HD ScatterResult scatter(const SceneAccess<SMEM> &sc, int prim, int last, float3 &o, float3 &d, float3 strike, uint32_t &colour,
                               Rng &rng, bool *inside_out) {
     const Material m = load_material(sc, prim);
     const bool is_plane = (m.flags & 2u) != 0;
+    const bool flipped = (m.flags & 1u) != 0;
+    const uint32_t style = m.style;
+
+    // ---- normal and inside flag: Sphere.fs:162-182 (F10); planes use their normal unflipped (F11) ----
+    float3 n;
+    bool inside = false;
     if (is_plane) {
         const DUnbounded &pl = sc.g.unb[prim - sc.g.n_bounded];
-        float3 n = f3(pl.n[0], pl.n[1], pl.n[2]);
-        if (inside_out) *inside_out = false;
-        switch (m.style) {
-        case RT_STYLE_LIGHT_SOURCE:
-            colour = combine(colour, m.texture < 0 ? m.rgb : texture_colour(sc.g, m.texture, strike));
-            return SCATTER_ABSORBED;
-        case RT_STYLE_FUZZED_REFLECTION: {
-            uint32_t nc = darken(m.albedo, combine(colour, m.rgb));
-            float3 pure = reflect_dir(n, d);
-            float3 out;
-            for (;;) {
-                float3 offset = unit_random(rng);
-                if (unitise(fma3(m.p0, offset, pure), out)) break;
-            }
-            colour = nc;
-            o = strike;
-            d = out;
-            return SCATTER_CONTINUE;
-        }
-        case RT_STYLE_LAMBERT_REFLECTION: {
-            float3 offset = unit_random(rng);
-            float3 out;
-            if (!unitise(n + offset, out)) return SCATTER_ERROR; // ValueOption.get throws, InfinitePlane.fs:86
-            colour = darken(m.albedo, combine(colour, m.rgb));
-            o = strike;
-            d = out;
-            return SCATTER_CONTINUE;
-        }
-        case RT_STYLE_PURE_REFLECTION:
-            colour = darken(m.albedo, combine(colour, m.rgb));
-            d = reflect_dir(n, d);
-            o = strike;
-            return SCATTER_CONTINUE;
-        default: return SCATTER_ERROR;
-        }
-    }
-
-    // ---- sphere prologue, Sphere.fs:162-182 (F10) ----
-    const bool flipped = (m.flags & 1u) != 0;
-    float3 n;
-    Cmp where;
-    float cx;
-    if (prim < sc.g.n_bounded) {
-        float4 s = sc.sphere(prim);
-        float3 v = f3(strike.x - s.x, strike.y - s.y, strike.z - s.z);
-        if (!unitise(v, n)) return SCATTER_ERROR; // Sphere.normal's ValueOption.get
-        float3 co = f3(s.x - o.x, s.y - o.y, s.z - o.z);
-        where = (prim == last) ? CMP_EQUAL : fcmp(dot(co, co), s.w * s.w);
-        cx = s.x;
+        n = f3(pl.n[0], pl.n[1], pl.n[2]);
     } else {
-        const DUnbounded &u = sc.g.unb[prim - sc.g.n_bounded];
-        D3 c{u.p[0], u.p[1], u.p[2]};
-        D3 v = d3(strike) - c;
-        double vv = dot(v, v);
-        if (fabs(vv) < kTolD) return SCATTER_ERROR;
-        double f = 1.0 / sqrt(vv);
-        n = f3(float(v.x * f), float(v.y * f), float(v.z * f));
-        D3 co = c - d3(o);
-        where = (prim == last) ? CMP_EQUAL : fcmp(dot(co, co), u.r2);
-        cx = float(u.p[0]);
-    }
-    bool inside = false;
-    if (where != CMP_GREATER) {
-        if (!flipped) { inside = true; n = -n; }
-    } else if (flipped) {
-        inside = true;
-        n = -n;
+        Cmp where;
+        if (prim < sc.g.n_bounded) {
+            float4 s = sc.sphere(prim);
+            float3 v = f3(strike.x - s.x, strike.y - s.y, strike.z - s.z);
+            if (!unitise(v, n)) return SCATTER_ERROR; // Sphere.normal's ValueOption.get
+            float3 co = f3(s.x - o.x, s.y - o.y, s.z - o.z);
+            where = (prim == last) ? CMP_EQUAL : fcmp(dot(co, co), s.w * s.w);
+        } else {
+            const DUnbounded &u = sc.g.unb[prim - sc.g.n_bounded];
+            D3 c{u.p[0], u.p[1], u.p[2]};
+            D3 v = d3(strike) - c;
+            float3 vf = f3(float(v.x), float(v.y), float(v.z)); // the subtraction is what needs FP64 (|c| ~ 1000)
+            if (!unitise(vf, n)) return SCATTER_ERROR;
+            D3 co = c - d3(o);
+            where = (prim == last) ? CMP_EQUAL : fcmp(dot(co, co), u.r2);
+        }
+        if (where != CMP_GREATER) {
+            if (!flipped) { inside = true; n = -n; }
+        } else if (flipped) {
+            inside = true;
+            n = -n;
+        }
     }
     if (inside_out) *inside_out = inside;
 
-    if (m.style == RT_STYLE_LIGHT_SOURCE) { // :185-189
+    // ---- emitters ----
+    if (style == RT_STYLE_LIGHT_SOURCE) { // Sphere.fs:185-189, InfinitePlane.fs:52-56
         colour = combine(colour, m.texture < 0 ? m.rgb : texture_colour(sc.g, m.texture, strike));
         return SCATTER_ABSORBED;
     }
-    if (m.style == RT_STYLE_LIGHT_SOURCE_CAP) { // :190-200; p0 = centre.x + (r - r / 4)
-        (void)cx;
+    if (style == RT_STYLE_LIGHT_SOURCE_CAP) { // Sphere.fs:190-200; p0 = centre.x + (r - r / 4)
         colour = (fcmp(strike.x, m.p0) == CMP_GREATER) ? combine(m.rgb, colour) : kBlack;
         return SCATTER_ABSORBED;
     }
-    const uint32_t nc = darken(m.albedo, combine(colour, m.texture < 0 ? m.rgb : texture_colour(sc.g, m.texture, strike)));
-    switch (m.style) {
-    case RT_STYLE_LAMBERT_REFLECTION: { // :202-222
-        float3 out;
-        for (;;) {
-            float3 offset = unit_random(rng);
-            if (unitise(n + offset, out)) break;
-        }
-        d = out;
-        break;
-    }
-    case RT_STYLE_PURE_REFLECTION: // :224-233
-        d = reflect_dir(n, d);
-        break;
-    case RT_STYLE_FUZZED_REFLECTION: { // :235-246 with addFuzz :89-104 (a fuzzed ray into the surface is kept, F11)
-        float3 pure = reflect_dir(n, d);
-        float3 out;
-        for (;;) {
-            float3 offset = unit_random(rng);
-            if (unitise(fma3(m.p0, offset, pure), out)) break;
-        }
-        d = out;
-        break;
-    }
-    case RT_STYLE_DIELECTRIC: { // :248-267
-        float u = rng.next().x;
-        if (u > m.p1)
-            d = reflect_dir(n, d);
-        else
-            d = refract_dir(inside, n, d, dot(d, n), m.p0);
-        break;
-    }
-    case RT_STYLE_GLASS: { // :269-300
-        float incoming_cos = -dot(d, n);
-        float u = rng.next().x;
+    if (style > RT_STYLE_GLASS || (is_plane && style > RT_STYLE_LAMBERT_REFLECTION)) return SCATTER_ERROR;
+
+    // ---- colour: darken albedo (combine incoming texture), Sphere.fs:203-207 etc., InfinitePlane.fs:40-41 ----
+    const uint32_t surface = (is_plane || m.texture < 0) ? m.rgb : texture_colour(sc.g, m.texture, strike);
+    const uint32_t nc = darken(m.albedo, combine(colour, surface));
+
+    // ---- the bounce's first RNG block, for every style that draws ----
+    float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (style != RT_STYLE_PURE_REFLECTION) u = rng.next();
+
+    // ---- mirror direction, for every style but Lambert ----
+    const float nd = dot(n, d);
+    const float3 tangent = fma3(-nd, n, d);
+    float3 refl = d;
+    if (style != RT_STYLE_LAMBERT_REFLECTION) refl = reflect_dir(n, d, nd, tangent);
+
+    float3 out = refl;      // PureReflection: Sphere.fs:224-233, InfinitePlane.fs:95-99
+    float3 base = n;        // Lambert: unit(n + offset), Sphere.fs:211-220, InfinitePlane.fs:78-86
+    float scale = 1.0f;
+    bool random_offset = (style == RT_STYLE_LAMBERT_REFLECTION);
+    if (style == RT_STYLE_FUZZED_REFLECTION) { // unit(reflected + fuzz * offset), Sphere.fs:89-104 (kept even if it points inwards, F11)
+        base = refl;
+        scale = m.p0;
+        random_offset = true;
+    } else if (style == RT_STYLE_DIELECTRIC) { // Sphere.fs:248-267
+        if (!(u.x > m.p1)) out = refract_dir(inside, n, d, tangent, refl, nd, m.p0);
+    } else if (style == RT_STYLE_GLASS) { // Sphere.fs:269-300
+        float incoming_cos = -nd;
         float refr = inside ? 1.0f / m.p0 : m.p0;
         float param = (1.0f - refr) / (1.0f + refr);
         param = param * param;
         float x = 1.0f - incoming_cos;
         float x2 = x * x;
         float reflection_prob = param + (1.0f - param) * (x2 * x2 * x);
-        if (u < reflection_prob)
-            d = reflect_dir(n, d);
-        else
-            d = refract_dir(inside, n, d, incoming_cos, m.p0);
-        break;
+        if (!(u.x < reflection_prob)) out = refract_dir(inside, n, d, tangent, refl, incoming_cos, m.p0);
     }
-    default: return SCATTER_ERROR;
+    if (random_offset) {
+        // UnitVector.random (Point.fs:49-59) redraws while |v|^2 < 1e-8; the callers redraw while the sum cannot be
+        // normalised — except InfinitePlane's Lambert, which takes one offset and throws (InfinitePlane.fs:86)
+        for (;;) {
+            float3 offset;
+            if (unitise(f3(2.0f * u.x - 1.0f, 2.0f * u.y - 1.0f, 2.0f * u.z - 1.0f), offset)) {
+                if (unitise(fma3(scale, offset, base), out)) break;
+                if (is_plane && style == RT_STYLE_LAMBERT_REFLECTION) return SCATTER_ERROR;
+            }
+            u = rng.next();
+        }
     }
     colour = nc;
     o = strike;
+    d = out;
     return SCATTER_CONTINUE;
 }
 

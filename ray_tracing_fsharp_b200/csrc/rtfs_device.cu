@@ -153,9 +153,10 @@ template <bool SMEM>
 __device__ __forceinline__ SceneAccess<SMEM> stage_scene(const FrameParams &fp) {
     SceneAccess<SMEM> sc;
     sc.g = fp.g;
-    sc.s_nodes = fp.s_nodes;
-    sc.s_spheres = fp.s_spheres;
-    sc.s_mats = fp.s_mats;
+    const uint32_t window = uint32_t(__cvta_generic_to_shared(rtfs_smem));
+    sc.s_nodes = window + 16u * fp.s_nodes;
+    sc.s_spheres = window + 16u * fp.s_spheres;
+    sc.s_mats = window + 16u * fp.s_mats;
     if (SMEM) {
         const int n_nodes_q = fp.g.n_nodes * 4, n_sph_q = fp.g.n_bounded, n_mat_q = (fp.g.n_bounded + fp.g.n_unbounded) * 2;
         for (int i = threadIdx.x; i < n_nodes_q; i += blockDim.x) rtfs_smem[fp.s_nodes + i] = __ldg(fp.g.nodes + i);
@@ -204,7 +205,7 @@ __device__ __forceinline__ void flush_counters(unsigned long long *counters, uin
 //   PROBE = false: item = 32 consecutive entries of the flagged-pixel list x one chunk of this rank's
 //                  share of the remaining sample indices (Scene.fs:191-192); sums are added atomically.
 template <bool PROBE, bool SMEM, bool COUNT>
-__global__ void __launch_bounds__(kBlockThreads) render_kernel(const FrameParams fp) {
+__global__ void __launch_bounds__(kBlockThreads, 1) render_kernel(const FrameParams fp) {
     const SceneAccess<SMEM> sc = stage_scene<SMEM>(fp);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpScratch *ws = reinterpret_cast<WarpScratch *>(rtfs_smem + fp.s_warp) + warp;
@@ -391,8 +392,8 @@ static int plan_launch(DeviceScene *ds, FrameParams &fp, bool probe, bool count,
     const size_t warp_q = (kBlockThreads / 32) * sizeof(WarpScratch) / 16;
     const size_t nodes_q = size_t(ds->g.n_nodes) * 4, sph_q = size_t(ds->g.n_bounded), mat_q = size_t(ds->g.n_bounded + ds->g.n_unbounded) * 2;
     const size_t scene_q = nodes_q + sph_q + mat_q;
-    // stage the scene in shared memory when two blocks per SM still fit beside it
-    bool smem = (scene_q + warp_q) * 16 <= 100 * 1024 && ds->g.n_bounded > 0;
+    // stage the scene in shared memory when it fits beside the per-warp scratch (one block per SM)
+    bool smem = (scene_q + warp_q) * 16 + 1024 <= ds->smem_optin && ds->g.n_bounded > 0;
     if (no_smem) smem = false;
     fp.s_nodes = 0;
     fp.s_spheres = uint32_t(nodes_q);

@@ -60,7 +60,7 @@ struct DeviceScene {
 
 
 constexpr int kTileW = 8, kTileH = 4; // a warp's 32 pixels
-constexpr int kBlockThreads = 256;
+constexpr int kBlockThreads = 768; // one persistent block per SM: 24 warps, at most 80 registers per thread
 
 struct FrameParams {
     SceneGlobal g;

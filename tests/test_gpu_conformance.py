@@ -106,7 +106,8 @@ def test_plane_hit_against_oracle():
     assert np.array_equal(np.isnan(want), np.isnan(got))
     hit = ~np.isnan(want)
     assert hit.sum() > 30_000
-    assert (np.abs(got[hit] - want[hit]) / want[hit]).max() <= 1e-10  # the device evaluates planes in FP64 (FMA contraction differs from the host in the last bits)
+    # numerator and denominator are FP64 on the device, the quotient FP32
+    assert (np.abs(got[hit] - want[hit]) / want[hit]).max() <= 1e-6
     # parallel ray and ray pointing away
     assert np.isnan(native.plane_hit([0, 1, 0], [1, 0, 0], [0, 0, 0], [0, 1, 0])[0])
     assert np.isnan(native.plane_hit([0, 1, 0], [0, 1, 0], [0, 0, 0], [0, 1, 0])[0])
