@@ -7,42 +7,88 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
 namespace rtfs {
 
-template <class T>
-static int upload(const std::vector<T> &v, T **out, size_t &bytes) {
+// ---------------------------------------------------------------------------------------------------
+// workspace pool
+// ---------------------------------------------------------------------------------------------------
+static std::mutex g_pool_mutex;
+static std::vector<DeviceWorkspace *> g_pool;
+
+static void workspace_destroy(DeviceWorkspace *ws) {
+    if (!ws) return;
+    cudaSetDevice(ws->device);
+    cudaFree(ws->d_stats);
+    cudaFree(ws->d_flags);
+    cudaFree(ws->d_rgb);
+    cudaFree(ws->d_list);
+    cudaFree(ws->d_counters);
+    if (ws->h_counters) cudaFreeHost(ws->h_counters);
+    for (auto &e : ws->ev)
+        if (e) cudaEventDestroy(e);
+    if (ws->stream) cudaStreamDestroy(ws->stream);
+    delete ws;
+}
+
+int workspace_acquire(int device, DeviceWorkspace **out) {
     *out = nullptr;
-    size_t n = std::max<size_t>(v.size(), 1);
-    RT_CUDA(cudaMalloc((void **)out, n * sizeof(T)));
-    if (!v.empty()) RT_CUDA(cudaMemcpy(*out, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
-    bytes += v.size() * sizeof(T);
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mutex);
+        for (size_t i = 0; i < g_pool.size(); ++i)
+            if (g_pool[i]->device == device) {
+                *out = g_pool[i];
+                g_pool.erase(g_pool.begin() + i);
+                return RT_OK;
+            }
+    }
+    auto *ws = new DeviceWorkspace();
+    ws->device = device;
+    cudaDeviceProp prop;
+    bool ok = cudaGetDeviceProperties(&prop, device) == cudaSuccess;
+    if (ok) {
+        ws->sm_count = prop.multiProcessorCount;
+        ws->smem_optin = prop.sharedMemPerBlockOptin;
+        ok = cudaMalloc((void **)&ws->d_counters, CN_SLOTS * sizeof(unsigned long long)) == cudaSuccess &&
+             cudaMallocHost((void **)&ws->h_counters, CN_SLOTS * sizeof(unsigned long long)) == cudaSuccess &&
+             cudaStreamCreateWithFlags(&ws->stream, cudaStreamNonBlocking) == cudaSuccess;
+        for (auto &e : ws->ev) ok = ok && cudaEventCreate(&e) == cudaSuccess;
+    }
+    if (!ok) {
+        std::string why = cudaGetErrorString(cudaGetLastError());
+        workspace_destroy(ws);
+        return fail(RT_ERR_CUDA, "device workspace allocation failed: " + why);
+    }
+    *out = ws;
     return RT_OK;
 }
 
+void workspace_release(DeviceWorkspace *ws) {
+    if (!ws) return;
+    cudaSetDevice(ws->device);
+    cudaStreamSynchronize(ws->stream);
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    if (g_pool.size() < 32) {
+        g_pool.push_back(ws);
+        return;
+    }
+    workspace_destroy(ws);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// device scene
+// ---------------------------------------------------------------------------------------------------
 void device_scene_free(RtScene *scene) {
     auto *ds = static_cast<DeviceScene *>(scene->dev);
     if (!ds) return;
     cudaSetDevice(ds->device);
+    if (ds->ws) workspace_release(ds->ws); // synchronises the stream first: nothing is still reading the scene
     for (auto t : ds->texobjs) cudaDestroyTextureObject(t);
     for (auto a : ds->arrays) cudaFreeArray(a);
-    cudaFree((void *)ds->g.nodes);
-    cudaFree((void *)ds->g.spheres);
-    cudaFree((void *)ds->g.mats);
-    cudaFree((void *)ds->g.unb);
-    cudaFree((void *)ds->g.tex);
-    cudaFree(ds->ref_nodes);
-    cudaFree(ds->d_stats);
-    cudaFree(ds->d_flags);
-    cudaFree(ds->d_rgb);
-    cudaFree(ds->d_list);
-    cudaFree(ds->d_counters);
-    if (ds->h_counters) cudaFreeHost(ds->h_counters);
-    for (auto &e : ds->ev)
-        if (e) cudaEventDestroy(e);
-    if (ds->stream) cudaStreamDestroy(ds->stream);
+    cudaFree(ds->blob);
     delete ds;
     scene->dev = nullptr;
 }
@@ -63,29 +109,7 @@ int device_scene_upload(RtScene *scene) {
         device_scene_free(scene);
         return code;
     };
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, ds->device) != cudaSuccess) return bail(fail(RT_ERR_CUDA, "cudaGetDeviceProperties failed"));
-    ds->sm_count = prop.multiProcessorCount;
-    ds->smem_optin = prop.sharedMemPerBlockOptin;
-
-    DNode *nodes = nullptr;
-    DSphere *spheres = nullptr;
-    DMaterial *mats = nullptr;
-    DUnbounded *unb = nullptr;
-    if ((rc = upload(L.nodes, &nodes, ds->bytes)) != RT_OK) return bail(rc);
-    ds->g.nodes = reinterpret_cast<const uint4 *>(nodes);
-    if ((rc = upload(L.spheres, &spheres, ds->bytes)) != RT_OK) return bail(rc);
-    ds->g.spheres = reinterpret_cast<const float4 *>(spheres);
-    if ((rc = upload(L.materials, &mats, ds->bytes)) != RT_OK) return bail(rc);
-    ds->g.mats = reinterpret_cast<const uint4 *>(mats);
-    if ((rc = upload(L.unbounded, &unb, ds->bytes)) != RT_OK) return bail(rc);
-    ds->g.unb = unb;
-    if ((rc = upload(L.ref_nodes, &ds->ref_nodes, ds->bytes)) != RT_OK) return bail(rc);
-    ds->n_ref_nodes = int32_t(L.ref_nodes.size());
-    ds->g.n_nodes = int32_t(L.nodes.size());
-    ds->g.n_bounded = L.n_bounded;
-    ds->g.n_unbounded = int32_t(L.unbounded.size());
-    ds->g.n_tex = int32_t(scene->textures.size());
+    if ((rc = workspace_acquire(ds->device, &ds->ws)) != RT_OK) return bail(rc);
 
     // textures: image texels go into a cudaArray read through a texture object (point sampling)
     std::vector<DTexture> dt(scene->textures.size());
@@ -133,16 +157,42 @@ int device_scene_upload(RtScene *scene) {
             ds->bytes += texels.size() * sizeof(uchar4);
         }
     }
-    DTexture *dtex = nullptr;
-    if ((rc = upload(dt, &dtex, ds->bytes)) != RT_OK) return bail(rc);
-    ds->g.tex = dtex;
 
-    if (cudaMalloc((void **)&ds->d_counters, CN_SLOTS * sizeof(unsigned long long)) != cudaSuccess ||
-        cudaMallocHost((void **)&ds->h_counters, CN_SLOTS * sizeof(unsigned long long)) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ds->stream, cudaStreamNonBlocking) != cudaSuccess)
-        return bail(fail(RT_ERR_CUDA, "scene scratch allocation failed"));
-    for (auto &e : ds->ev)
-        if (cudaEventCreate(&e) != cudaSuccess) return bail(fail(RT_ERR_CUDA, "cudaEventCreate failed"));
+    // everything else travels as one blob: one allocation, one host->device copy
+    auto align = [](size_t x) { return (x + 255) & ~size_t(255); };
+    const size_t off_nodes = 0;
+    const size_t off_spheres = align(off_nodes + L.nodes.size() * sizeof(DNode));
+    const size_t off_mats = align(off_spheres + L.spheres.size() * sizeof(DSphere));
+    const size_t off_unb = align(off_mats + L.materials.size() * sizeof(DMaterial));
+    const size_t off_ref = align(off_unb + L.unbounded.size() * sizeof(DUnbounded));
+    const size_t off_tex = align(off_ref + L.ref_nodes.size() * sizeof(DRefNode));
+    const size_t total = align(off_tex + dt.size() * sizeof(DTexture)) + 256;
+    std::vector<uint8_t> host(total, 0);
+    auto put = [&](size_t off, const void *src, size_t n) {
+        if (n) std::memcpy(host.data() + off, src, n);
+    };
+    put(off_nodes, L.nodes.data(), L.nodes.size() * sizeof(DNode));
+    put(off_spheres, L.spheres.data(), L.spheres.size() * sizeof(DSphere));
+    put(off_mats, L.materials.data(), L.materials.size() * sizeof(DMaterial));
+    put(off_unb, L.unbounded.data(), L.unbounded.size() * sizeof(DUnbounded));
+    put(off_ref, L.ref_nodes.data(), L.ref_nodes.size() * sizeof(DRefNode));
+    put(off_tex, dt.data(), dt.size() * sizeof(DTexture));
+    if (cudaMalloc(&ds->blob, total) != cudaSuccess) return bail(fail(RT_ERR_CUDA, "cudaMalloc failed for the scene"));
+    if (cudaMemcpy(ds->blob, host.data(), total, cudaMemcpyHostToDevice) != cudaSuccess)
+        return bail(fail(RT_ERR_CUDA, "host->device copy of the scene failed"));
+    ds->bytes += total;
+    uint8_t *base = static_cast<uint8_t *>(ds->blob);
+    ds->g.nodes = reinterpret_cast<const uint4 *>(base + off_nodes);
+    ds->g.spheres = reinterpret_cast<const float4 *>(base + off_spheres);
+    ds->g.mats = reinterpret_cast<const uint4 *>(base + off_mats);
+    ds->g.unb = reinterpret_cast<const DUnbounded *>(base + off_unb);
+    ds->ref_nodes = reinterpret_cast<DRefNode *>(base + off_ref);
+    ds->g.tex = reinterpret_cast<const DTexture *>(base + off_tex);
+    ds->n_ref_nodes = int32_t(L.ref_nodes.size());
+    ds->g.n_nodes = int32_t(L.nodes.size());
+    ds->g.n_bounded = L.n_bounded;
+    ds->g.n_unbounded = int32_t(L.unbounded.size());
+    ds->g.n_tex = int32_t(scene->textures.size());
     return RT_OK;
 }
 
@@ -393,7 +443,7 @@ static int plan_launch(DeviceScene *ds, FrameParams &fp, bool probe, bool count,
     const size_t nodes_q = size_t(ds->g.n_nodes) * 4, sph_q = size_t(ds->g.n_bounded), mat_q = size_t(ds->g.n_bounded + ds->g.n_unbounded) * 2;
     const size_t scene_q = nodes_q + sph_q + mat_q;
     // stage the scene in shared memory when it fits beside the per-warp scratch (one block per SM)
-    bool smem = (scene_q + warp_q) * 16 + 1024 <= ds->smem_optin && ds->g.n_bounded > 0;
+    bool smem = (scene_q + warp_q) * 16 + 1024 <= ds->ws->smem_optin && ds->g.n_bounded > 0;
     if (no_smem) smem = false;
     fp.s_nodes = 0;
     fp.s_spheres = uint32_t(nodes_q);
@@ -406,17 +456,17 @@ static int plan_launch(DeviceScene *ds, FrameParams &fp, bool probe, bool count,
     int per_sm = 0;
     RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)fn, kBlockThreads, plan.smem_bytes));
     if (per_sm < 1) return fail(RT_ERR_CUDA, "render kernel does not fit on an SM");
-    plan.blocks = per_sm * ds->sm_count;
+    plan.blocks = per_sm * ds->ws->sm_count;
     return RT_OK;
 }
 
 static int ensure_list(DeviceScene *ds, size_t n_pixels) {
-    if (ds->list_pixels >= n_pixels) return RT_OK;
-    cudaFree(ds->d_list);
-    ds->d_list = nullptr;
-    ds->list_pixels = 0;
-    RT_CUDA(cudaMalloc((void **)&ds->d_list, n_pixels * sizeof(uint32_t)));
-    ds->list_pixels = n_pixels;
+    if (ds->ws->list_pixels >= n_pixels) return RT_OK;
+    cudaFree(ds->ws->d_list);
+    ds->ws->d_list = nullptr;
+    ds->ws->list_pixels = 0;
+    RT_CUDA(cudaMalloc((void **)&ds->ws->d_list, n_pixels * sizeof(uint32_t)));
+    ds->ws->list_pixels = n_pixels;
     return RT_OK;
 }
 
@@ -442,7 +492,7 @@ void fill_frame(FrameParams &fp, DeviceScene *ds, const RtCamera &cam, int max_w
         fp.sample_begin = 0;
         fp.sample_end = cam.samples_per_pixel;
     }
-    fp.counters = ds->d_counters;
+    fp.counters = ds->ws->d_counters;
 }
 
 // picks the samples-per-item of the main phase: enough items to balance the persistent warps, long
@@ -456,7 +506,7 @@ static int pick_chunk(int n_local, size_t n_pixels, int resident_warps) {
 }
 
 int launch_probe(DeviceScene *ds, FrameParams fp, bool count, bool no_smem, cudaStream_t st, int *launches) {
-    RT_CUDA(cudaMemsetAsync(ds->d_counters + CN_WORK_PROBE, 0, sizeof(unsigned long long), st));
+    RT_CUDA(cudaMemsetAsync(ds->ws->d_counters + CN_WORK_PROBE, 0, sizeof(unsigned long long), st));
     LaunchPlan plan;
     RenderKernelFn fn;
     int rc = plan_launch(ds, fp, true, count, no_smem, plan, fn);
@@ -471,12 +521,12 @@ int launch_main(DeviceScene *ds, FrameParams fp, const FlagsView &flags, bool co
     const size_t n_pixels = size_t(fp.cam.rows) * fp.cam.cols;
     int rc = ensure_list(ds, n_pixels);
     if (rc != RT_OK) return rc;
-    RT_CUDA(cudaMemsetAsync(ds->d_counters + CN_LIST, 0, sizeof(unsigned long long), st));
-    RT_CUDA(cudaMemsetAsync(ds->d_counters + CN_WORK_MAIN, 0, sizeof(unsigned long long), st));
-    compact_kernel<<<ds->sm_count * 4, 256, 0, st>>>(flags, ds->d_list, ds->d_counters, fp.cam.rows, fp.cam.cols, fp.tiles_x, fp.tiles_y);
+    RT_CUDA(cudaMemsetAsync(ds->ws->d_counters + CN_LIST, 0, sizeof(unsigned long long), st));
+    RT_CUDA(cudaMemsetAsync(ds->ws->d_counters + CN_WORK_MAIN, 0, sizeof(unsigned long long), st));
+    compact_kernel<<<ds->ws->sm_count * 4, 256, 0, st>>>(flags, ds->ws->d_list, ds->ws->d_counters, fp.cam.rows, fp.cam.cols, fp.tiles_x, fp.tiles_y);
     RT_CUDA(cudaGetLastError());
     ++*launches;
-    fp.list = ds->d_list;
+    fp.list = ds->ws->d_list;
     LaunchPlan plan;
     RenderKernelFn fn;
     rc = plan_launch(ds, fp, false, count, no_smem, plan, fn);
@@ -493,11 +543,11 @@ int launch_main(DeviceScene *ds, FrameParams fp, const FlagsView &flags, bool co
 }
 
 void read_counters(DeviceScene *ds, RtStats *stats, size_t n_pixels, bool adaptive) {
-    stats->paths = ds->h_counters[CN_PATHS];
-    stats->rays = ds->h_counters[CN_RAYS];
-    stats->box_tests = ds->h_counters[CN_BOX];
-    stats->prim_tests = ds->h_counters[CN_PRIM];
-    stats->pixels_early_out = adaptive ? (unsigned long long)n_pixels - ds->h_counters[CN_LIST] : 0;
+    stats->paths = ds->ws->h_counters[CN_PATHS];
+    stats->rays = ds->ws->h_counters[CN_RAYS];
+    stats->box_tests = ds->ws->h_counters[CN_BOX];
+    stats->prim_tests = ds->ws->h_counters[CN_PRIM];
+    stats->pixels_early_out = adaptive ? (unsigned long long)n_pixels - ds->ws->h_counters[CN_LIST] : 0;
 }
 
 // implemented in rtfs_wavefront.cu
@@ -536,7 +586,7 @@ int rt_device_probe(RtScene *scene, const RtCamera *camera, int32_t max_w, int32
     fp.flags = d_flags;
     const size_t n_pixels = size_t(fp.cam.rows) * fp.cam.cols;
     int launches = 0;
-    RT_CUDA(cudaMemsetAsync(ds->d_counters, 0, CN_SLOTS * sizeof(unsigned long long), st));
+    RT_CUDA(cudaMemsetAsync(ds->ws->d_counters, 0, CN_SLOTS * sizeof(unsigned long long), st));
     if (!fp.adaptive) {
         // no probe phase: every pixel takes all its samples in the main phase (rank 0 raises the flags once)
         if (rank == 0) RT_CUDA(cudaMemsetAsync(d_flags, 1, n_pixels, st));
@@ -545,7 +595,7 @@ int rt_device_probe(RtScene *scene, const RtCamera *camera, int32_t max_w, int32
         if (rc != RT_OK) return rc;
     }
     if (stats) {
-        RT_CUDA(cudaMemcpyAsync(ds->h_counters, ds->d_counters, CN_SLOTS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        RT_CUDA(cudaMemcpyAsync(ds->ws->h_counters, ds->ws->d_counters, CN_SLOTS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         RT_CUDA(cudaStreamSynchronize(st));
         std::memset(stats, 0, sizeof *stats);
         read_counters(ds, stats, n_pixels, false);
@@ -571,7 +621,7 @@ int rt_device_main(RtScene *scene, const RtCamera *camera, int32_t max_w, int32_
     rc = launch_main(ds, fp, single_flags(d_flags), (opts->flags & RT_FLAG_COUNTERS) != 0, (opts->flags & RT_FLAG_NO_SMEM) != 0, st, &launches);
     if (rc != RT_OK) return rc;
     if (stats) {
-        RT_CUDA(cudaMemcpyAsync(ds->h_counters, ds->d_counters, CN_SLOTS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        RT_CUDA(cudaMemcpyAsync(ds->ws->h_counters, ds->ws->d_counters, CN_SLOTS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         RT_CUDA(cudaStreamSynchronize(st));
         std::memset(stats, 0, sizeof *stats);
         read_counters(ds, stats, n_pixels, fp.adaptive != 0);
@@ -587,14 +637,14 @@ int rt_device_counters(RtScene *scene, void *stream, RtStats *stats) {
     auto *ds = static_cast<DeviceScene *>(scene->dev);
     RT_CUDA(cudaSetDevice(ds->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    RT_CUDA(cudaMemcpyAsync(ds->h_counters, ds->d_counters, CN_SLOTS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    RT_CUDA(cudaMemcpyAsync(ds->ws->h_counters, ds->ws->d_counters, CN_SLOTS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     RT_CUDA(cudaStreamSynchronize(st));
     std::memset(stats, 0, sizeof *stats);
-    stats->paths = ds->h_counters[CN_PATHS];
-    stats->rays = ds->h_counters[CN_RAYS];
-    stats->box_tests = ds->h_counters[CN_BOX];
-    stats->prim_tests = ds->h_counters[CN_PRIM];
-    stats->pixels_early_out = ds->h_counters[CN_LIST]; // NOTE: here the number of pixels that went on to phase 2
+    stats->paths = ds->ws->h_counters[CN_PATHS];
+    stats->rays = ds->ws->h_counters[CN_RAYS];
+    stats->box_tests = ds->ws->h_counters[CN_BOX];
+    stats->prim_tests = ds->ws->h_counters[CN_PRIM];
+    stats->pixels_early_out = ds->ws->h_counters[CN_LIST]; // NOTE: here the number of pixels that went on to phase 2
     return RT_OK;
 }
 
@@ -617,54 +667,54 @@ int rt_render(RtScene *scene, const RtCamera *camera, int32_t max_w, int32_t max
     auto *ds = static_cast<DeviceScene *>(scene->dev);
     RT_CUDA(cudaSetDevice(ds->device));
     const size_t n_pixels = size_t(2 * max_w + 1) * size_t(2 * max_h + 1);
-    if (ds->ws_pixels < n_pixels) {
-        cudaFree(ds->d_stats);
-        cudaFree(ds->d_flags);
-        cudaFree(ds->d_rgb);
-        ds->d_stats = nullptr;
-        ds->d_flags = nullptr;
-        ds->d_rgb = nullptr;
-        ds->ws_pixels = 0;
-        RT_CUDA(cudaMalloc((void **)&ds->d_stats, n_pixels * 4 * sizeof(int32_t)));
-        RT_CUDA(cudaMalloc((void **)&ds->d_flags, n_pixels));
-        RT_CUDA(cudaMalloc((void **)&ds->d_rgb, n_pixels * 3));
-        ds->ws_pixels = n_pixels;
+    if (ds->ws->ws_pixels < n_pixels) {
+        cudaFree(ds->ws->d_stats);
+        cudaFree(ds->ws->d_flags);
+        cudaFree(ds->ws->d_rgb);
+        ds->ws->d_stats = nullptr;
+        ds->ws->d_flags = nullptr;
+        ds->ws->d_rgb = nullptr;
+        ds->ws->ws_pixels = 0;
+        RT_CUDA(cudaMalloc((void **)&ds->ws->d_stats, n_pixels * 4 * sizeof(int32_t)));
+        RT_CUDA(cudaMalloc((void **)&ds->ws->d_flags, n_pixels));
+        RT_CUDA(cudaMalloc((void **)&ds->ws->d_rgb, n_pixels * 3));
+        ds->ws->ws_pixels = n_pixels;
     }
-    cudaStream_t st = ds->stream;
+    cudaStream_t st = ds->ws->stream;
     FrameParams fp;
     fill_frame(fp, ds, *camera, max_w, max_h, *opts, 0, 1);
-    fp.stats = ds->d_stats;
-    fp.flags = ds->d_flags;
+    fp.stats = ds->ws->d_stats;
+    fp.flags = ds->ws->d_flags;
     const bool count = (opts->flags & RT_FLAG_COUNTERS) != 0, no_smem = (opts->flags & RT_FLAG_NO_SMEM) != 0;
     int launches = 0;
-    RT_CUDA(cudaEventRecord(ds->ev[0], st));
-    RT_CUDA(cudaMemsetAsync(ds->d_counters, 0, CN_SLOTS * sizeof(unsigned long long), st));
-    RT_CUDA(cudaMemsetAsync(ds->d_stats, 0, n_pixels * 4 * sizeof(int32_t), st));
-    RT_CUDA(cudaEventRecord(ds->ev[1], st));
+    RT_CUDA(cudaEventRecord(ds->ws->ev[0], st));
+    RT_CUDA(cudaMemsetAsync(ds->ws->d_counters, 0, CN_SLOTS * sizeof(unsigned long long), st));
+    RT_CUDA(cudaMemsetAsync(ds->ws->d_stats, 0, n_pixels * 4 * sizeof(int32_t), st));
+    RT_CUDA(cudaEventRecord(ds->ws->ev[1], st));
     if (fp.adaptive) {
         rc = launch_probe(ds, fp, count, no_smem, st, &launches);
         if (rc != RT_OK) return rc;
     } else {
-        RT_CUDA(cudaMemsetAsync(ds->d_flags, 1, n_pixels, st));
+        RT_CUDA(cudaMemsetAsync(ds->ws->d_flags, 1, n_pixels, st));
     }
-    rc = launch_main(ds, fp, single_flags(ds->d_flags), count, no_smem, st, &launches);
+    rc = launch_main(ds, fp, single_flags(ds->ws->d_flags), count, no_smem, st, &launches);
     if (rc != RT_OK) return rc;
-    RT_CUDA(cudaEventRecord(ds->ev[2], st));
-    finalize_kernel<<<unsigned((n_pixels + 255) / 256), 256, 0, st>>>(ds->d_stats, int(n_pixels), opts->gamma, ds->d_rgb);
+    RT_CUDA(cudaEventRecord(ds->ws->ev[2], st));
+    finalize_kernel<<<unsigned((n_pixels + 255) / 256), 256, 0, st>>>(ds->ws->d_stats, int(n_pixels), opts->gamma, ds->ws->d_rgb);
     RT_CUDA(cudaGetLastError());
     ++launches;
-    RT_CUDA(cudaMemcpyAsync(rgb_out, ds->d_rgb, n_pixels * 3, cudaMemcpyDeviceToHost, st));
-    if (sums_out) RT_CUDA(cudaMemcpyAsync(sums_out, ds->d_stats, n_pixels * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    RT_CUDA(cudaMemcpyAsync(ds->h_counters, ds->d_counters, CN_SLOTS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    RT_CUDA(cudaEventRecord(ds->ev[3], st));
+    RT_CUDA(cudaMemcpyAsync(rgb_out, ds->ws->d_rgb, n_pixels * 3, cudaMemcpyDeviceToHost, st));
+    if (sums_out) RT_CUDA(cudaMemcpyAsync(sums_out, ds->ws->d_stats, n_pixels * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    RT_CUDA(cudaMemcpyAsync(ds->ws->h_counters, ds->ws->d_counters, CN_SLOTS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    RT_CUDA(cudaEventRecord(ds->ws->ev[3], st));
     RT_CUDA(cudaStreamSynchronize(st));
     if (stats) {
         std::memset(stats, 0, sizeof *stats);
         read_counters(ds, stats, n_pixels, fp.adaptive != 0);
         float ms = 0.f;
-        cudaEventElapsedTime(&ms, ds->ev[1], ds->ev[2]);
+        cudaEventElapsedTime(&ms, ds->ws->ev[1], ds->ws->ev[2]);
         stats->kernel_ms = ms;
-        cudaEventElapsedTime(&ms, ds->ev[0], ds->ev[3]);
+        cudaEventElapsedTime(&ms, ds->ws->ev[0], ds->ws->ev[3]);
         stats->total_ms = ms;
         stats->launches = launches;
     }

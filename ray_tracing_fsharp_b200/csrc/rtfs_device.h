@@ -34,30 +34,38 @@ inline int require_device(int device) {
 // ---------------------------------------------------------------------------------------------------
 enum CounterSlot { CN_PATHS = 0, CN_RAYS = 1, CN_BOX = 2, CN_PRIM = 3, CN_LIST = 4, CN_WORK_PROBE = 5, CN_WORK_MAIN = 6, CN_SLOTS = 8 };
 
-struct DeviceScene {
+// Frame buffers, scratch, stream and events of one device.  Allocating these costs milliseconds, so they are
+// pooled: a scene handle borrows one for its lifetime and returns it on destroy (handles stay independent of
+// one another; nothing is shared between two live handles).
+struct DeviceWorkspace {
     int device = 0;
-    SceneGlobal g{};
-    DRefNode *ref_nodes = nullptr;
-    int32_t n_ref_nodes = 0;
-    std::vector<cudaArray_t> arrays;
-    std::vector<cudaTextureObject_t> texobjs;
-    size_t bytes = 0;
     int sm_count = 0;
     size_t smem_optin = 0;
-    // frame workspace owned by the handle (rt_render)
-    size_t ws_pixels = 0;
+    size_t ws_pixels = 0; // frame buffers of rt_render
     int32_t *d_stats = nullptr;
     uint8_t *d_flags = nullptr;
     uint8_t *d_rgb = nullptr;
-    // per-call scratch (any entry point)
-    size_t list_pixels = 0;
+    size_t list_pixels = 0; // flagged-pixel list of the main phase
     uint32_t *d_list = nullptr;
     unsigned long long *d_counters = nullptr;
     unsigned long long *h_counters = nullptr; // pinned
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
+int workspace_acquire(int device, DeviceWorkspace **out);
+void workspace_release(DeviceWorkspace *ws);
 
+struct DeviceScene {
+    int device = 0;
+    SceneGlobal g{};
+    DRefNode *ref_nodes = nullptr;
+    int32_t n_ref_nodes = 0;
+    void *blob = nullptr; // one allocation holding nodes | spheres | materials | unbounded | reference nodes | textures
+    std::vector<cudaArray_t> arrays;
+    std::vector<cudaTextureObject_t> texobjs;
+    size_t bytes = 0;
+    DeviceWorkspace *ws = nullptr;
+};
 
 constexpr int kTileW = 8, kTileH = 4; // a warp's 32 pixels
 constexpr int kBlockThreads = 768; // one persistent block per SM: 24 warps, at most 80 registers per thread

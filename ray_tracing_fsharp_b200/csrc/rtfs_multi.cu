@@ -228,7 +228,7 @@ int rt_multi_render(RtMulti *m, const RtCamera *camera, int32_t max_w, int32_t m
         fps[i].stats = m->d_stats[i];
         fps[i].flags = m->d_flags[i];
         RT_CUDA(cudaEventRecord(m->ev_begin[i], st));
-        RT_CUDA(cudaMemsetAsync(ds->d_counters, 0, CN_SLOTS * sizeof(unsigned long long), st));
+        RT_CUDA(cudaMemsetAsync(ds->ws->d_counters, 0, CN_SLOTS * sizeof(unsigned long long), st));
         RT_CUDA(cudaMemsetAsync(m->d_stats[i], 0, n_pixels * 4 * sizeof(int32_t), st));
         if (fps[i].adaptive) {
             RT_CUDA(cudaMemsetAsync(m->d_flags[i], 0, n_pixels, st));
@@ -248,7 +248,7 @@ int rt_multi_render(RtMulti *m, const RtCamera *camera, int32_t max_w, int32_t m
             if (j != i) RT_CUDA(cudaStreamWaitEvent(st, m->ev_probe[j], 0));
         rc = launch_main(ds, fps[i], flags, count, no_smem, st, &launches[i]);
         if (rc != RT_OK) return rc;
-        RT_CUDA(cudaMemcpyAsync(ds->h_counters, ds->d_counters, CN_SLOTS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        RT_CUDA(cudaMemcpyAsync(ds->ws->h_counters, ds->ws->d_counters, CN_SLOTS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         RT_CUDA(cudaEventRecord(m->ev_main[i], st));
     }
     // reduce + finalize: needs everyone's sums; each device owns a slice of the pixels
@@ -288,11 +288,11 @@ int rt_multi_render(RtMulti *m, const RtCamera *camera, int32_t max_w, int32_t m
         unsigned long long listed = 0;
         for (int i = 0; i < world; ++i) {
             auto *ds = static_cast<DeviceScene *>(m->scenes[i]->dev);
-            stats->paths += ds->h_counters[CN_PATHS];
-            stats->rays += ds->h_counters[CN_RAYS];
-            stats->box_tests += ds->h_counters[CN_BOX];
-            stats->prim_tests += ds->h_counters[CN_PRIM];
-            listed = ds->h_counters[CN_LIST];
+            stats->paths += ds->ws->h_counters[CN_PATHS];
+            stats->rays += ds->ws->h_counters[CN_RAYS];
+            stats->box_tests += ds->ws->h_counters[CN_BOX];
+            stats->prim_tests += ds->ws->h_counters[CN_PRIM];
+            listed = ds->ws->h_counters[CN_LIST];
             stats->launches += launches[i];
             float ms = 0.f;
             cudaEventElapsedTime(&ms, m->ev_begin[i], m->ev_end[i]);
