@@ -354,7 +354,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--counters", action="store_true", help="also report box / primitive tests per ray of the device traversal")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
-    ap.add_argument("--flops-per-ray", type=float, default=0.0)
+    ap.add_argument("--flops-per-ray", type=float, default=414.0, help="FLOPs of the reference traversal per ray on C2 (DESIGN.md); used when the CPU sample does not run")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
