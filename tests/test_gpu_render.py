@@ -79,6 +79,25 @@ def test_shared_memory_and_global_memory_kernels_agree_bit_for_bit():
     assert not np.array_equal(sa, sd)  # the seed matters
 
 
+@pytest.mark.parametrize("which", ["reduced", "C1", "C3", "C4"])
+def test_wavefront_and_megakernel_agree_bit_for_bit(which):
+    """RT_MODE_WAVEFRONT runs the same device functions on a different schedule (queues in HBM, one launch pair per
+    bounce): identical RNG keys and integer sums => identical accumulators, adaptive and not."""
+    if which == "reduced":
+        spec = small_random_spheres()
+    else:
+        spec = _small(which, 48, 27, 24)
+    osc, dsc, cam = scene_pair(spec)
+    mw, mh = spec.max_width_coord, spec.max_height_coord
+    for adaptive in (True, False):
+        a, sa, sta = dsc.render(cam, mw, mh, seed=41, adaptive=adaptive, want_sums=True)
+        b, sb, stb = dsc.render(cam, mw, mh, seed=41, adaptive=adaptive, want_sums=True, mode=abi.RT_MODE_WAVEFRONT)
+        assert np.array_equal(sa, sb) and np.array_equal(a, b)
+        assert int(sta.rays) == int(stb.rays) and int(sta.paths) == int(stb.paths)
+        assert int(sta.pixels_early_out) == int(stb.pixels_early_out)
+        assert stb.launches > sta.launches
+
+
 def test_hot_pink_when_the_bounce_budget_runs_out():
     """F3: a path that is still alive after maxCount + 1 interactions is HotPink, a miss is Black."""
     from ray_tracing_fsharp_b200.domain import Colour, Hittable, Pixel, Sphere, SphereStyle, Texture
