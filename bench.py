@@ -318,7 +318,7 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(spec, adaptive), "l2": "flushed between steps (256 MiB fill)",
                        "parallelism": f"sample-split x{world}" + (", NCCL all-reduce of flags (max) and sums (int32 sum)" if world > 1 else ""),
-                       "scene_in_shared_memory": not args.no_smem},
+                       "scene_bytes_staged_in_shared_memory": 0 if args.no_smem else scene.shared_memory_bytes()},
             "rays_per_step": rays / args.steps, "paths_per_step": paths / args.steps,
             "e2e": {"value": e2e_rays / e2e_secs / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * e2e_secs / n_e2e, "steps": n_e2e,

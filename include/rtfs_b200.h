@@ -187,6 +187,9 @@ int rt_scene_bvh_nodes(const RtScene *scene, int32_t which, double *bounds, int3
                        int32_t *prim);
 /* bytes of scene data resident on the device (nodes + primitives + materials + textures) */
 size_t rt_scene_device_bytes(const RtScene *scene);
+/* bytes of BVH + spheres + materials that every persistent block stages in shared memory; 0 when the scene
+ * is too large for that and is read from global memory (L1 / L2) instead */
+size_t rt_scene_shared_memory_bytes(const RtScene *scene);
 
 /* ---- render (host buffers) ------------------------------------------------------------------ */
 

@@ -572,6 +572,16 @@ int rt_device_count(void) {
     return n;
 }
 
+// bytes of the scene each persistent block stages in shared memory (0: the BVH is read from global memory / L2)
+size_t rt_scene_shared_memory_bytes(const RtScene *scene) {
+    if (!scene || !scene->dev) return 0;
+    auto *ds = static_cast<const DeviceScene *>(scene->dev);
+    const size_t warp_q = (kBlockThreads / 32) * sizeof(WarpScratch) / 16;
+    const size_t scene_q = size_t(ds->g.n_nodes) * 4 + size_t(ds->g.n_bounded) + size_t(ds->g.n_bounded + ds->g.n_unbounded) * 2;
+    bool smem = (scene_q + warp_q) * 16 + 1024 <= ds->ws->smem_optin && ds->g.n_bounded > 0;
+    return smem ? scene_q * 16 : 0;
+}
+
 int rt_device_probe(RtScene *scene, const RtCamera *camera, int32_t max_w, int32_t max_h, const RtRenderOpts *opts, int32_t rank,
                     int32_t world, int32_t *d_stats, uint8_t *d_flags, void *stream, RtStats *stats) {
     int rc = check_frame_args(scene, camera, max_w, max_h, opts);

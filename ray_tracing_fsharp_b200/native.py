@@ -42,6 +42,7 @@ def _declare(lib):
         "rt_scene_bvh_node_count": (C.c_int, [_vp, _i32]),
         "rt_scene_bvh_nodes": (C.c_int, [_vp, _i32, _vp, _vp, _vp]),
         "rt_scene_device_bytes": (C.c_size_t, [_vp]),
+        "rt_scene_shared_memory_bytes": (C.c_size_t, [_vp]),
         "rt_render": (C.c_int, [_vp, C.POINTER(RtCamera), _i32, _i32, C.POINTER(RtRenderOpts), _vp, _vp, C.POINTER(RtStats)]),
         "rt_render_multi": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _i32, C.POINTER(RtCamera), _i32, _i32, C.POINTER(RtRenderOpts), _vp,
                                       _vp, C.POINTER(RtStats)]),
@@ -150,6 +151,9 @@ class SceneHandle:
 
     def device_bytes(self):
         return int(lib().rt_scene_device_bytes(self.ptr))
+
+    def shared_memory_bytes(self):
+        return int(lib().rt_scene_shared_memory_bytes(self.ptr))
 
     # ---- render ----
     def render(self, camera, max_w, max_h, seed=0, adaptive=True, mode=abi.RT_MODE_MEGAKERNEL, gamma=False, flags=0,
