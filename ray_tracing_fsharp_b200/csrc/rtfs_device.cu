@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -26,6 +27,7 @@ static void workspace_destroy(DeviceWorkspace *ws) {
     cudaFree(ws->d_flags);
     cudaFree(ws->d_rgb);
     cudaFree(ws->d_list);
+    cudaFree(ws->d_stats_b);
     cudaFree(ws->d_counters);
     if (ws->h_counters) cudaFreeHost(ws->h_counters);
     for (auto &e : ws->ev)
@@ -217,12 +219,18 @@ __device__ __forceinline__ SceneAccess<SMEM> stage_scene(const FrameParams &fp) 
     return sc;
 }
 
-// per-warp scratch in shared memory: a pool cursor and two sets of 32x3 integer accumulators
+// per-warp scratch in shared memory: two item slots (one being issued, one whose last paths are still in flight)
+struct ItemSlot {
+    int cursor;    // next path of the item's pool
+    int j_begin;   // first local sample index of the item's chunk
+    int j_len;     // samples in the chunk (also what the flush adds to the pixels' count field)
+    int to_b;      // probe: the chunk belongs to the second accumulator set
+    int pix[32];   // row << 16 | col of each of the 32 pixels, -1: none
+    int gpix[32];  // row * cols + col of the same pixels, -1: none
+    int acc[3][32];
+};
 struct WarpScratch {
-    int cursor;
-    int pad[3];
-    int pix[32];
-    int acc[2][3][32];
+    ItemSlot slot[2];
 };
 static_assert(sizeof(WarpScratch) % 16 == 0, "WarpScratch must be a multiple of 16 bytes");
 
@@ -245,15 +253,17 @@ __device__ __forceinline__ void flush_counters(unsigned long long *counters, uin
     }
 }
 
-// The render kernel.  Persistent warps pull work items from a global cursor; an item is 32 pixels times a
-// run of sample indices.  Inside an item the 32 lanes pull (pixel, sample) paths from a warp-local pool, so
-// every lane traces until the pool is dry (path regeneration) and per-sample results are added to the
-// pixel's integer accumulators in shared memory (PixelStats.add, Pixel.fs:87-95).
-//   PROBE = true : item = one 8x4 tile owned by this rank; paths = the 2*firstTrial+1 probe samples of
-//                  renderPixel (Scene.fs:172-182); writes the sums, and flags pixels whose two truncated
-//                  means differ (Scene.fs:183-188).
-//   PROBE = false: item = 32 consecutive entries of the flagged-pixel list x one chunk of this rank's
-//                  share of the remaining sample indices (Scene.fs:191-192); sums are added atomically.
+// The render kernel.  Persistent warps pull work items from a global cursor; an item is a unit of 32 pixels
+// times a chunk of sample indices.  Inside an item the 32 lanes pull (pixel, sample) paths from a warp-local pool,
+// so every lane traces until the pool is dry (path regeneration); per-sample results are added to the pixels'
+// integer accumulators in shared memory (PixelStats.add, Pixel.fs:87-95) and flushed with one RED per channel.
+//   PROBE = true : unit = one 8x4 tile owned by this rank; samples = the 2*firstTrial+1 probe samples of
+//                  renderPixel (Scene.fs:172-182): those up to firstTrial go to `stats`, the rest to `stats_b`
+//                  (no chunk straddles the two), so that probe_flags_kernel can compare the two means.
+//   PROBE = false: unit = 32 consecutive entries of the flagged-pixel list; samples = this rank's share of the
+//                  remaining sample indices (Scene.fs:191-192).
+// A warp issues one instruction every ~7.6 cycles whatever the load, so the kernel ends one whole item after the
+// work runs out: hence chunks of decreasing length, the last ones a single sample (see build_chunks).
 template <bool PROBE, bool SMEM, bool COUNT>
 __global__ void __launch_bounds__(kBlockThreads, 1) render_kernel(const FrameParams fp) {
     const SceneAccess<SMEM> sc = stage_scene<SMEM>(fp);
@@ -263,107 +273,142 @@ __global__ void __launch_bounds__(kBlockThreads, 1) render_kernel(const FramePar
     uint32_t n_paths = 0, n_rays = 0;
     TraversalCounters cn{0, 0};
 
-    // main-phase geometry of the sample split: this rank owns sample_begin + rank + j * world
-    const int n_span = fp.sample_end - fp.sample_begin - fp.rank;
-    const int n_local = PROBE ? fp.n_probe : (n_span > 0 ? (n_span + fp.world - 1) / fp.world : 0);
-    const int n_chunks = PROBE ? 1 : (n_local + fp.chunk - 1) / fp.chunk;
     const unsigned n_list = PROBE ? 0u : (unsigned)fp.counters[CN_LIST];
-    const unsigned long long n_items =
-        PROBE ? (unsigned long long)((fp.tiles_x * fp.tiles_y - fp.rank + fp.world - 1) / fp.world)
-              : (unsigned long long)((n_list + 31u) / 32u) * (unsigned long long)n_chunks;
+    const unsigned n_units = PROBE ? unsigned((fp.tiles_x * fp.tiles_y - fp.rank + fp.world - 1) / fp.world) : (n_list + 31u) / 32u;
+    const unsigned long long n_items = (unsigned long long)n_units * (unsigned long long)fp.n_chunks;
 
-    for (;;) {
-        unsigned long long item = 0;
-        if (lane == 0) item = atomicAdd(work, 1ull);
-        item = __shfl_sync(0xffffffffu, item, 0);
-        if (item >= n_items) break;
-
-        // ---- decode the item: this lane's pixel, and the pool ----
-        int my_pixel = -1; // row_idx * cols + col_idx of the pixel this lane finalises
-        int n_entries, j_begin, j_len;
+    // Loads work item `item` into a slot: chunk-major numbering; this lane's pixel; the pool.  Returns the pool size.
+    auto load_item = [&](ItemSlot *sl, unsigned long long item, int &n_entries) -> int {
+        const int k = int(item / n_units);
+        const unsigned unit = unsigned(item - (unsigned long long)k * n_units);
+        const int j_begin = fp.chunk_begin[k], j_len = fp.chunk_len[k];
+        int my_pixel = -1;
+        n_entries = 32;
         if (PROBE) {
-            int tile = int(item) * fp.world + fp.rank;
+            int tile = int(unit) * fp.world + fp.rank;
             int ty = tile / fp.tiles_x, tx = tile - ty * fp.tiles_x;
             int r = ty * kTileH + (lane >> 3), c = tx * kTileW + (lane & 7);
             if (r < fp.cam.rows && c < fp.cam.cols) my_pixel = r * fp.cam.cols + c;
-            n_entries = 32;
-            j_begin = 0;
-            j_len = fp.n_probe;
         } else {
-            unsigned seg = unsigned(item / (unsigned long long)n_chunks);
-            int chunk = int(item - (unsigned long long)seg * n_chunks);
-            unsigned e = seg * 32u + lane;
+            unsigned e = unit * 32u + lane;
             if (e < n_list) my_pixel = int(fp.list[e]);
-            n_entries = int(min(32u, n_list - seg * 32u));
-            j_begin = chunk * fp.chunk;
-            j_len = min(fp.chunk, n_local - j_begin);
+            n_entries = int(min(32u, n_list - unit * 32u));
         }
-        ws->acc[0][0][lane] = 0; ws->acc[0][1][lane] = 0; ws->acc[0][2][lane] = 0;
-        if (PROBE) { ws->acc[1][0][lane] = 0; ws->acc[1][1][lane] = 0; ws->acc[1][2][lane] = 0; }
-        ws->pix[lane] = my_pixel < 0 ? -1 : (((my_pixel / fp.cam.cols) << 16) | (my_pixel % fp.cam.cols));
-        if (lane == 0) ws->cursor = 0;
+        sl->acc[0][lane] = 0; sl->acc[1][lane] = 0; sl->acc[2][lane] = 0;
+        sl->gpix[lane] = my_pixel;
+        sl->pix[lane] = my_pixel < 0 ? -1 : (((my_pixel / fp.cam.cols) << 16) | (my_pixel % fp.cam.cols));
+        if (lane == 0) {
+            sl->cursor = 0;
+            sl->j_begin = j_begin;
+            sl->j_len = j_len;
+            sl->to_b = (PROBE && j_begin > fp.first_trial) ? 1 : 0;
+        }
         __syncwarp();
-        const int pool = n_entries * j_len;
+        return n_entries * j_len;
+    };
+    // Retires a slot whose paths have all finished: one RED per channel and pixel (PixelStats.add, Pixel.fs:87-95)
+    auto flush_item = [&](ItemSlot *sl) {
+        __syncwarp();
+        int px = sl->gpix[lane];
+        if (px >= 0) {
+            int *st = (sl->to_b ? fp.stats_b : fp.stats) + 4 * size_t(px);
+            atomicAdd(st + 0, sl->acc[0][lane]);
+            atomicAdd(st + 1, sl->acc[1][lane]);
+            atomicAdd(st + 2, sl->acc[2][lane]);
+            atomicAdd(st + 3, sl->j_len);
+        }
+        __syncwarp();
+    };
+    auto fetch_item = [&]() -> unsigned long long { // lane 0 pulls the next item number; consumed (shuffled) later
+        return lane == 0 ? atomicAdd(work, 1ull) : 0ull;
+    };
 
-        // ---- drain the pool ----
-        // No lane leaves this loop before the whole warp is done: the full-mask vote below is the point where the
-        // warp reconverges every iteration (lanes that regenerate a path and lanes that do not would otherwise drift
-        // apart for good, and the traversal would run at a fraction of the warp width).
+    unsigned long long item = __shfl_sync(0xffffffffu, fetch_item(), 0);
+    if (item < n_items) {
+        // Two slots per warp: lanes pull paths from slot `cur`; when its pool is dry the next item is loaded into the
+        // other slot straight away (as soon as that slot's last in-flight paths have finished and it has been flushed),
+        // so lanes do not idle while the last paths of an item complete.  Only the warp's final item drains.
+        int cur = 0;
+        bool other_holds = false, finishing = false;
+        int n_entries;
+        int pool = load_item(&ws->slot[0], item, n_entries);
+        int j_begin = ws->slot[0].j_begin;
+        unsigned long long prefetched = fetch_item();
         PathState ps;
         bool active = false, dry = false;
-        int slot = 0, set = 0;
+        int lane_slot = 0, my = 0; // my: slot index of this lane's path; lane_slot: its pixel within the item
         for (;;) {
             if (!active && !dry) {
-                int q = atomicAdd(&ws->cursor, 1);
+                ItemSlot *sl = &ws->slot[cur];
+                int q = atomicAdd(&sl->cursor, 1);
                 if (q >= pool) {
                     dry = true;
                 } else {
-                    int j = q / n_entries;
-                    slot = q - j * n_entries;
-                    int rc = ws->pix[slot]; // row << 16 | col, or -1 where the tile overhangs the image edge
+                    int j = (n_entries == 32) ? (q >> 5) : (q / n_entries);
+                    lane_slot = q - j * n_entries;
+                    my = cur;
+                    int rc = sl->pix[lane_slot]; // row << 16 | col, or -1 where the tile overhangs the image edge
                     if (rc >= 0) {
-                        uint32_t sample = uint32_t(PROBE ? j : fp.sample_begin + fp.rank + (j_begin + j) * fp.world);
-                        set = (PROBE && j > fp.first_trial) ? 1 : 0;
+                        uint32_t sample = uint32_t(PROBE ? j_begin + j : fp.sample_begin + fp.rank + (j_begin + j) * fp.world);
                         ++n_paths;
                         active = path_begin(ps, fp.cam, fp.k0, fp.k1, rc >> 16, rc & 0xffff, sample); // false: Ray.make' failed (the reference throws)
                     }
                 }
             }
-            if (!__any_sync(0xffffffffu, active || !dry)) break;
+            // Every lane votes, every iteration: this is where the warp reconverges (lanes that regenerate a path and lanes
+            // that do not would otherwise drift apart for good and the traversal would run at a fraction of the warp width).
+            if (__any_sync(0xffffffffu, dry)) {
+                // the current pool is exhausted: move on as soon as the other slot is free
+                if (!finishing && !__any_sync(0xffffffffu, active && my != cur)) {
+                    ItemSlot *other = &ws->slot[cur ^ 1];
+                    if (other_holds) flush_item(other);
+                    item = __shfl_sync(0xffffffffu, prefetched, 0);
+                    if (item < n_items) {
+                        pool = load_item(other, item, n_entries);
+                        j_begin = other->j_begin;
+                        prefetched = fetch_item();
+                        cur ^= 1;
+                        other_holds = true; // the slot we just left still has paths in flight
+                        dry = false;
+                    } else {
+                        other_holds = false;
+                        finishing = true;
+                    }
+                }
+                if (finishing && !__any_sync(0xffffffffu, active)) break;
+            }
             if (active) {
                 uint32_t result;
                 ++n_rays;
                 if (path_step<SMEM, COUNT>(ps, sc, fp.cam.depth, result, cn)) {
-                    atomicAdd(&ws->acc[set][0][slot], int((result >> 16) & 255u));
-                    atomicAdd(&ws->acc[set][1][slot], int((result >> 8) & 255u));
-                    atomicAdd(&ws->acc[set][2][slot], int(result & 255u));
+                    int *acc = &ws->slot[my].acc[0][0];
+                    atomicAdd(acc + lane_slot, int((result >> 16) & 255u));
+                    atomicAdd(acc + 32 + lane_slot, int((result >> 8) & 255u));
+                    atomicAdd(acc + 64 + lane_slot, int(result & 255u));
                     active = false;
                 }
             }
         }
-        __syncwarp();
-
-        // ---- retire the item ----
-        if (my_pixel >= 0) {
-            if (PROBE) {
-                int a0 = ws->acc[0][0][lane], a1 = ws->acc[0][1][lane], a2 = ws->acc[0][2][lane];
-                int b0 = a0 + ws->acc[1][0][lane], b1 = a1 + ws->acc[1][1][lane], b2 = a2 + ws->acc[1][2][lane];
-                int n_old = fp.first_trial + 1, n_new = fp.n_probe;
-                // PixelStats.mean (Pixel.fs:103-108): truncating integer division; Pixel.difference :113-116
-                int diff = abs(b0 / n_new - a0 / n_old) + abs(b1 / n_new - a1 / n_old) + abs(b2 / n_new - a2 / n_old);
-                reinterpret_cast<int4 *>(fp.stats)[my_pixel] = make_int4(b0, b1, b2, n_new);
-                fp.flags[my_pixel] = (diff != 0 && fp.sample_end > fp.sample_begin) ? 1 : 0;
-            } else {
-                int *st = fp.stats + 4 * size_t(my_pixel);
-                atomicAdd(st + 0, ws->acc[0][0][lane]);
-                atomicAdd(st + 1, ws->acc[0][1][lane]);
-                atomicAdd(st + 2, ws->acc[0][2][lane]);
-                atomicAdd(st + 3, j_len);
-            }
-        }
-        __syncwarp();
+        flush_item(&ws->slot[cur]); // `finishing` was set after the other slot had been flushed
     }
     flush_counters(fp.counters, n_paths, n_rays, cn, COUNT);
+}
+
+// End of the probe phase (Scene.fs:177-188) for the tiles this rank owns: merge the two accumulator sets into
+// `stats`, flag the pixels whose two truncated means differ (PixelStats.mean Pixel.fs:103-108, Pixel.difference :113-116)
+__global__ void probe_flags_kernel(int32_t *stats, const int32_t *stats_b, uint8_t *flags, int rows, int cols, int tiles_x, int rank, int world,
+                                   int first_trial, int n_probe, int more) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= rows * cols) return;
+    int r = p / cols, c = p - r * cols;
+    int tile = (r / kTileH) * tiles_x + c / kTileW;
+    if (tile % world != rank) return;
+    int4 a = reinterpret_cast<int4 *>(stats)[p], b = reinterpret_cast<const int4 *>(stats_b)[p];
+    int n_old = first_trial + 1;
+    int4 s = make_int4(a.x + b.x, a.y + b.y, a.z + b.z, n_probe);
+    int diff = abs(s.x / n_probe - a.x / n_old) + abs(s.y / n_probe - a.y / n_old) + abs(s.z / n_probe - a.z / n_old);
+    reinterpret_cast<int4 *>(stats)[p] = s;
+    flags[p] = (diff != 0 && more) ? 1 : 0;
 }
 
 // flags -> list of flagged pixel ids, one warp per 8x4 tile so that list neighbours are image neighbours
@@ -495,23 +540,79 @@ void fill_frame(FrameParams &fp, DeviceScene *ds, const RtCamera &cam, int max_w
     fp.counters = ds->ws->d_counters;
 }
 
-// picks the samples-per-item of the main phase: enough items to balance the persistent warps, long
-// enough runs that the tail of a pool (lanes idling on the last paths) stays small
-static int pick_chunk(int n_local, size_t n_pixels, int resident_warps) {
-    if (n_local <= 0) return 1;
-    size_t segs = (n_pixels + 31) / 32;
-    int chunk = 64;
-    while (chunk > 8 && segs * size_t((n_local + chunk - 1) / chunk) < size_t(resident_warps) * 24) chunk /= 2;
-    return std::min(chunk, std::max(1, n_local));
+// Cuts this rank's local sample range [0, n_local) into chunks: `bulk` samples per chunk, then a taper
+// bulk/2, bulk/4, ..., 2, 1, 1 so that the last layers of items are short (a warp cannot be sped up, so the
+// kernel ends one item after the work runs out).  No chunk straddles `boundary` (probe: firstTrial + 1, the first
+// sample of the second accumulator set).  Chunks are stored by decreasing length: items are numbered chunk-major.
+static void build_chunks(FrameParams &fp, int n_local, int boundary, size_t n_units, int resident_warps) {
+    fp.n_chunks = 0;
+    if (n_local <= 0) return;
+    // bulk chunk: every warp should see ~16 bulk items; at most 32 samples (1024 paths) per item
+    long long bulk = (long long)(n_units * size_t(n_local)) / (16LL * std::max(1, resident_warps));
+    bulk = std::max(1LL, std::min(32LL, bulk));
+    if (const char *e = std::getenv("RTFS_BULK")) bulk = std::max(1, std::atoi(e)); // experiment knob
+    bulk = std::max(bulk, (long long)((n_local + 159) / 160)); // the table has kMaxChunks entries
+    std::vector<int> sizes;
+    for (int t = int(bulk) / 2; t >= 1; t /= 2) sizes.push_back(t);
+    if (bulk > 1) sizes.push_back(1);
+    int taper = 0;
+    for (int t : sizes) taper += t;
+    while (!sizes.empty() && taper > n_local) { // short range: drop the longest taper chunks
+        taper -= sizes.front();
+        sizes.erase(sizes.begin());
+    }
+    int rest = n_local - taper;
+    std::vector<int> all;
+    while (rest > 0) {
+        int c = int(std::min<long long>(bulk, rest));
+        all.push_back(c);
+        rest -= c;
+    }
+    all.insert(all.end(), sizes.begin(), sizes.end());
+    std::vector<std::pair<int, int>> chunks;
+    int at = 0;
+    for (int c : all) {
+        if (boundary > at && boundary < at + c) { // split at the boundary
+            chunks.push_back({at, boundary - at});
+            chunks.push_back({boundary, at + c - boundary});
+        } else {
+            chunks.push_back({at, c});
+        }
+        at += c;
+    }
+    std::stable_sort(chunks.begin(), chunks.end(), [](const std::pair<int, int> &a, const std::pair<int, int> &b) { return a.second > b.second; });
+    fp.n_chunks = int(std::min<size_t>(chunks.size(), kMaxChunks));
+    for (int k = 0; k < fp.n_chunks; ++k) {
+        fp.chunk_begin[k] = uint16_t(chunks[k].first);
+        fp.chunk_len[k] = uint16_t(chunks[k].second);
+    }
 }
 
 int launch_probe(DeviceScene *ds, FrameParams fp, bool count, bool no_smem, cudaStream_t st, int *launches) {
-    RT_CUDA(cudaMemsetAsync(ds->ws->d_counters + CN_WORK_PROBE, 0, sizeof(unsigned long long), st));
+    DeviceWorkspace *ws = ds->ws;
+    const size_t n_pixels = size_t(fp.cam.rows) * fp.cam.cols;
+    if (ws->probe_pixels < n_pixels) {
+        cudaFree(ws->d_stats_b);
+        ws->d_stats_b = nullptr;
+        ws->probe_pixels = 0;
+        RT_CUDA(cudaMalloc((void **)&ws->d_stats_b, n_pixels * 4 * sizeof(int32_t)));
+        ws->probe_pixels = n_pixels;
+    }
+    RT_CUDA(cudaMemsetAsync(ws->d_stats_b, 0, n_pixels * 4 * sizeof(int32_t), st));
+    RT_CUDA(cudaMemsetAsync(ws->d_counters + CN_WORK_PROBE, 0, sizeof(unsigned long long), st));
+    fp.stats_b = ws->d_stats_b;
     LaunchPlan plan;
     RenderKernelFn fn;
     int rc = plan_launch(ds, fp, true, count, no_smem, plan, fn);
     if (rc != RT_OK) return rc;
+    const size_t n_units = size_t((fp.tiles_x * fp.tiles_y - fp.rank + fp.world - 1) / fp.world);
+    build_chunks(fp, fp.n_probe, fp.first_trial + 1, n_units, plan.blocks * (kBlockThreads / 32));
     fn<<<plan.blocks, kBlockThreads, plan.smem_bytes, st>>>(fp);
+    RT_CUDA(cudaGetLastError());
+    ++*launches;
+    probe_flags_kernel<<<unsigned((n_pixels + 255) / 256), 256, 0, st>>>(fp.stats, ws->d_stats_b, fp.flags, fp.cam.rows, fp.cam.cols, fp.tiles_x,
+                                                                          fp.rank, fp.world, fp.first_trial, fp.n_probe,
+                                                                          fp.sample_end > fp.sample_begin ? 1 : 0);
     RT_CUDA(cudaGetLastError());
     ++*launches;
     return RT_OK;
@@ -533,7 +634,8 @@ int launch_main(DeviceScene *ds, FrameParams fp, const FlagsView &flags, bool co
     if (rc != RT_OK) return rc;
     int n_span = fp.sample_end - fp.sample_begin - fp.rank;
     int n_local = n_span > 0 ? (n_span + fp.world - 1) / fp.world : 0;
-    fp.chunk = pick_chunk(n_local, n_pixels, plan.blocks * (kBlockThreads / 32));
+    // the list length is only known on the device; size the chunks for the whole frame (an upper bound on the units)
+    build_chunks(fp, n_local, -1, (n_pixels + 31) / 32, plan.blocks * (kBlockThreads / 32));
     if (n_local > 0) {
         fn<<<plan.blocks, kBlockThreads, plan.smem_bytes, st>>>(fp);
         RT_CUDA(cudaGetLastError());

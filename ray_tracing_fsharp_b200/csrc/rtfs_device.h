@@ -41,6 +41,8 @@ struct DeviceWorkspace {
     int device = 0;
     int sm_count = 0;
     size_t smem_optin = 0;
+    size_t probe_pixels = 0; // second accumulator set of the probe phase
+    int32_t *d_stats_b = nullptr;
     size_t ws_pixels = 0; // frame buffers of rt_render
     int32_t *d_stats = nullptr;
     uint8_t *d_flags = nullptr;
@@ -68,6 +70,7 @@ struct DeviceScene {
 };
 
 constexpr int kTileW = 8, kTileH = 4; // a warp's 32 pixels
+constexpr int kMaxChunks = 192;
 constexpr int kBlockThreads = 768; // one persistent block per SM: 24 warps, at most 80 registers per thread
 
 struct FrameParams {
@@ -80,9 +83,15 @@ struct FrameParams {
     int32_t n_probe;      // 2 * first_trial + 1
     int32_t sample_begin; // first sample index of the main phase
     int32_t sample_end;   // one past the last
-    int32_t chunk;        // samples per main-phase work item
     int32_t adaptive;
+    // work items: (unit, chunk k) where a unit is 32 pixels and chunk k covers this rank's local sample indices
+    // [chunk_begin[k], chunk_begin[k] + chunk_len[k]); chunks are sorted by decreasing length and items are
+    // numbered chunk-major, so the persistent warps meet the long items first and the short ones last
+    int32_t n_chunks;
+    uint16_t chunk_begin[kMaxChunks];
+    uint16_t chunk_len[kMaxChunks];
     int32_t *stats;       // rows*cols*4 {sumR, sumG, sumB, count}
+    int32_t *stats_b;     // probe phase: sums of the samples after the first firstTrial + 1 (same layout)
     uint8_t *flags;       // rows*cols
     const uint32_t *list; // flagged pixel ids (main phase)
     unsigned long long *counters;
