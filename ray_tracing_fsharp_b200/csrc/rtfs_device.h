@@ -71,7 +71,7 @@ struct DeviceScene {
 
 constexpr int kTileW = 8, kTileH = 4; // a warp's 32 pixels
 constexpr int kMaxChunks = 192;
-constexpr int kBlockThreads = 768; // one persistent block per SM: 24 warps, at most 80 registers per thread
+constexpr int kBlockThreads = 1024; // one persistent block per SM: 32 warps at 64 registers per thread (issue-bound kernel: more warps per scheduler pays)
 
 struct FrameParams {
     SceneGlobal g;
