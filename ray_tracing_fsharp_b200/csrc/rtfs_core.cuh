@@ -185,7 +185,8 @@ RTFS_HD RaySlabs make_slabs(float3 o, float3 d) {
     float y = fabsf(d.y) < tiny ? copysignf(tiny, d.y) : d.y;
     float z = fabsf(d.z) < tiny ? copysignf(tiny, d.z) : d.z;
     RaySlabs r;
-    r.inv = f3(1.0f / x, 1.0f / y, 1.0f / z);
+    // approximate reciprocals (1 ulp): the slab test is padded, and noi is built from the same inv
+    r.inv = f3(__fdividef(1.0f, x), __fdividef(1.0f, y), __fdividef(1.0f, z));
     r.noi = f3(-o.x * r.inv.x, -o.y * r.inv.y, -o.z * r.inv.z);
     r.pad = 4.8e-7f * fmaxf(fmaxf(fabsf(r.noi.x), fabsf(r.noi.y)), fabsf(r.noi.z));
     return r;

@@ -60,7 +60,7 @@ class DeviceBackend:
     def probe(self, rank, world, stats, flags):
         native.check(native.lib().rt_device_probe(self.scene.ptr, C.byref(self.camera), self.max_w, self.max_h, C.byref(self.opts), rank,
                                                   world, C.c_void_p(stats.data_ptr()), C.c_void_p(flags.data_ptr()), self._stream(), None))
-        self.launches += 1 if self.opts.adaptive else 0
+        self.launches += 2 if self.opts.adaptive else 0  # probe + probe_flags
 
     def main(self, rank, world, stats, flags):
         native.check(native.lib().rt_device_main(self.scene.ptr, C.byref(self.camera), self.max_w, self.max_h, C.byref(self.opts), rank,
