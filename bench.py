@@ -250,7 +250,7 @@ def run_ours(args):
     e2e_rays = 0
     h2d = d2h = 0
     n_e2e = max(1, min(args.steps, 3))
-    for i in range(n_e2e):
+    for i in range(-1, n_e2e):  # iteration -1 is an untimed warm-up (first-use allocations of a fresh handle)
         barrier()
         t0 = time.perf_counter()
         if world == 1:
@@ -280,8 +280,9 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
             dist.all_reduce(rr, op=dist.ReduceOp.SUM)
-        e2e_secs += float(dt.item())
-        e2e_rays += int(rr.item())
+        if i >= 0:
+            e2e_secs += float(dt.item())
+            e2e_rays += int(rr.item())
 
     # one extra, untimed frame with the traversal counters on (a slower kernel variant): tests per ray of OUR traversal
     traversal = None

@@ -96,7 +96,7 @@ __global__ void k_hit_object(SceneGlobal g, const DRefNode *ref_nodes, int n_ref
         sc.g = g;
         sc.s_nodes = sc.s_spheres = sc.s_mats = 0;
         TraversalCounters cn{0, 0};
-        h = closest_hit<false, false>(sc, ld3(o, i), ld3(d, i), kNoPrim, cn);
+        h = closest_hit<false, false>(sc, ld3(o, i), ld3(d, i), kNoPrim, cn, 1u << (threadIdx.x & 31));
     }
     if (h.prim == kNoPrim) {
         prim_out[i] = -1;
@@ -184,7 +184,7 @@ __global__ void k_trace_samples(SceneGlobal g, DevCamera cam, uint32_t k0, uint3
     if (path_begin(ps, cam, k0, k1, row_idx[i], col_idx[i], uint32_t(sample[i]))) {
         for (;;) {
             ++rays;
-            if (path_step<false, false>(ps, sc, cam.depth, result, cn)) break;
+            if (path_step<false, false>(ps, sc, cam.depth, result, cn, 1u << (threadIdx.x & 31))) break; // lanes run independently here
         }
     }
     colour_out[3 * i] = uint8_t(result >> 16);

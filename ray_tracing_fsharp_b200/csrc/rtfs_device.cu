@@ -377,10 +377,11 @@ __global__ void __launch_bounds__(kBlockThreads, 1) render_kernel(const FramePar
                 }
                 if (finishing && !__any_sync(0xffffffffu, active)) break;
             }
+            const unsigned tracing = __ballot_sync(0xffffffffu, active);
             if (active) {
                 uint32_t result;
                 ++n_rays;
-                if (path_step<SMEM, COUNT>(ps, sc, fp.cam.depth, result, cn)) {
+                if (path_step<SMEM, COUNT>(ps, sc, fp.cam.depth, result, cn, tracing)) {
                     int *acc = &ws->slot[my].acc[0][0];
                     atomicAdd(acc + lane_slot, int((result >> 16) & 255u));
                     atomicAdd(acc + 32 + lane_slot, int((result >> 8) & 255u));

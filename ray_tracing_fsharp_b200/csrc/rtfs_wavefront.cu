@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(kWfThreads) wf_extend(const WfParams p) {
             p.st.hit[slot] = make_uint2(0u, uint32_t(kNoPrim));
             continue;
         }
-        Hit h = closest_hit<SMEM, false>(sc, f3(a.x, a.y, a.z), f3(a.w, b.x, b.y), last, cn);
+        Hit h = closest_hit<SMEM, false>(sc, f3(a.x, a.y, a.z), f3(a.w, b.x, b.y), last, cn, 1u << (threadIdx.x & 31));
         ++rays;
         p.st.hit[slot] = make_uint2(__float_as_uint(h.t), uint32_t(h.prim));
     }
