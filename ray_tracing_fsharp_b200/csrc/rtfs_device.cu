@@ -6,7 +6,6 @@
 
 #include <algorithm>
 #include <cstdio>
-#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -551,7 +550,6 @@ static void build_chunks(FrameParams &fp, int n_local, int boundary, size_t n_un
     // bulk chunk: every warp should see ~16 bulk items; at most 32 samples (1024 paths) per item
     long long bulk = (long long)(n_units * size_t(n_local)) / (16LL * std::max(1, resident_warps));
     bulk = std::max(1LL, std::min(32LL, bulk));
-    if (const char *e = std::getenv("RTFS_BULK")) bulk = std::max(1, std::atoi(e)); // experiment knob
     bulk = std::max(bulk, (long long)((n_local + 159) / 160)); // the table has kMaxChunks entries
     std::vector<int> sizes;
     for (int t = int(bulk) / 2; t >= 1; t /= 2) sizes.push_back(t);

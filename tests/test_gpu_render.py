@@ -248,3 +248,27 @@ def test_errors_are_codes_not_crashes():
     assert b"mode" in lib.rt_last_error()
     with pytest.raises(native.RtError):
         native.SceneHandle([], [], 99)
+
+
+def test_edge_sizes_and_budgets():
+    """Smallest frame (3x3), one sample, zero bounce budget, a frame that is not a multiple of the 8x4 tile, and a
+    frame with fewer pixels than one warp — each against the oracle with the shared RNG."""
+    spec = _small("C1", 1, 1, 1)
+    osc, dsc, cam = scene_pair(spec)
+    for max_w, max_h, spp, depth, adaptive in [(1, 1, 1, 50, True), (1, 1, 3, 0, True), (5, 3, 12, 2, True), (13, 2, 7, 50, False),
+                                               (2, 9, 16, 1, True)]:
+        cam.samples_per_pixel, cam.bounce_depth = spp, depth
+        ref, ref_stats, counters, _ = osc.render(cam, max_w, max_h, seed=3, rng_mode=1, adaptive=adaptive)
+        rgb, sums, stats = dsc.render(cam, max_w, max_h, seed=3, adaptive=adaptive, want_sums=True)
+        assert rgb.shape == (2 * max_h + 1, 2 * max_w + 1, 3)
+        assert np.array_equal(sums[..., 3], ref_stats[..., 3])
+        assert (sums == ref_stats).all(2).mean() > 0.95 and np.abs(rgb.astype(int) - ref.astype(int)).max() <= 40
+        assert int(stats.paths) == counters["paths"]
+        b, sb, _ = dsc.render(cam, max_w, max_h, seed=3, adaptive=adaptive, want_sums=True, mode=abi.RT_MODE_WAVEFRONT)
+        assert np.array_equal(sb, sums)
+    cam.bounce_depth = 0  # maxCount = 0: one interaction; anything that does not hit an emitter straight away is HotPink
+    cam.samples_per_pixel = 4
+    rgb, sums, stats = dsc.render(cam, 10, 6, seed=1, adaptive=False, want_sums=True)
+    assert int(stats.rays) == int(stats.paths)
+    hot = (rgb == np.array([205, 105, 180], np.uint8)).all(2)
+    assert hot.any() and not hot.all()
