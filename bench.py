@@ -200,9 +200,24 @@ def run_ours(args):
     def red_sum(t):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
 
-    def frame(seed):
+    main_events = []
+
+    def frame(seed, time_main=False):
+        """probe -> [all-reduce flags] -> compact + main -> [all-reduce sums] -> finalize on rank 0 (distributed.py)."""
         backend.opts.seed = seed
-        stats, _ = render_split_frame(backend, rank, world, red_max, red_sum)
+        stats, flags = backend.alloc()
+        backend.probe(rank, world, stats, flags)
+        if world > 1:
+            red_max(flags)
+        if time_main:  # the dominant kernel, for the roofline: events on the stream the kernels are launched on
+            m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            m0.record()
+        backend.main(rank, world, stats, flags)
+        if time_main:
+            m1.record()
+            main_events.append((m0, m1))
+        if world > 1:
+            red_sum(stats)
         return backend.finalize(stats) if rank == 0 else None
 
     fp32_peak = native.measure_fp32_peak(local_rank) if rank == 0 else 0.0
@@ -224,7 +239,7 @@ def run_ours(args):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        frame(2000 + i)
+        frame(2000 + i, time_main=True)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -244,6 +259,14 @@ def run_ours(args):
         dist.all_reduce(launch_t, op=dist.ReduceOp.SUM)
     secs = ms_total / 1e3
     value = rays / secs / 1e6
+    # the main-phase kernel alone (rank 0's launches): its share of the rays comes from an untimed probe-only frame
+    main_ms = sum(a.elapsed_time(b) for a, b in main_events) / max(1, len(main_events))
+    backend.opts.seed = 2000 + args.steps - 1
+    ps_, pf_ = backend.alloc()
+    backend.probe(rank, world, ps_, pf_)
+    probe_rays_rank0 = backend.counters().rays
+    backend.main(rank, world, ps_, pf_)
+    main_rays_rank0 = backend.counters().rays - probe_rays_rank0
 
     # ---- end to end through the public API with host buffers ----
     e2e_secs = 0.0
@@ -304,7 +327,7 @@ def run_ours(args):
         # algorithmic FLOPs per ray of the REFERENCE traversal on this scene: measured by the oracle on the CPU
         # sample when it ran, else the figure recorded in DESIGN.md for C2
         f_ray = flops_per_ray(cpu["counters"]) if cpu else args.flops_per_ray
-        achieved = rays / secs * f_ray / 1e12
+        achieved = main_rays_rank0 / (main_ms / 1e3) * f_ray / 1e12
         traffic = None
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tp):
@@ -328,8 +351,10 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak if fp32_peak else None,
                          "traffic": traffic, "flops_per_ray": f_ray,
-                         "note": "achieved = rays/s x FLOPs the REFERENCE traversal spends per ray (exhaustive DFS, SURVEY §8d); peak = FP32 FMA "
-                                 "microbenchmark measured in this run (MEASURED_PEAKS.json has no FP32 figure)"},
+                         "kernel": "render_kernel<PROBE=0> (main phase), rank 0", "kernel_ms_per_launch": main_ms, "rays_per_launch": main_rays_rank0,
+                         "note": "achieved = rays per launch x FLOPs the REFERENCE traversal spends per ray (exhaustive DFS, SURVEY 8d) / CUDA-event "
+                                 "duration of the launch; peak = FP32 FMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP32 "
+                                 "figure); traffic = DRAM bytes per launch, ncu, profiles/roofline_traffic.json"},
         }
         if traversal:
             line["traversal"] = traversal
