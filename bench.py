@@ -265,6 +265,8 @@ def run_ours(args):
     ps_, pf_ = backend.alloc()
     backend.probe(rank, world, ps_, pf_)
     probe_rays_rank0 = backend.counters().rays
+    if world > 1:
+        red_max(pf_)
     backend.main(rank, world, ps_, pf_)
     main_rays_rank0 = backend.counters().rays - probe_rays_rank0
 
