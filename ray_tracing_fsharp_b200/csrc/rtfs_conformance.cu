@@ -297,6 +297,7 @@ int rt_test_hit_object(RtScene *scene, int32_t traversal, int32_t n, const doubl
     RT_TRY(scene_device(scene, &ds));
     if (n < 0 || !origin || !dir || !prim_out || !t_out) return fail(RT_ERR_INVALID_ARGUMENT, "rt_test_hit_object: bad argument");
     if (traversal != 0 && traversal != 1) return fail(RT_ERR_INVALID_ARGUMENT, "rt_test_hit_object: traversal must be 0 or 1");
+    if (traversal == 1) RT_TRY(device_scene_ensure_reference(scene));
     DevBuf<float> o, d, t, s;
     DevBuf<int32_t> p;
     RT_TRY(o.put(to_f32(origin, 3 * size_t(n))));

@@ -79,6 +79,49 @@ void workspace_release(DeviceWorkspace *ws) {
     workspace_destroy(ws);
 }
 
+// Image textures: cudaMallocArray / cudaCreateTextureObject / their destructors cost milliseconds to tens of
+// milliseconds, so arrays are pooled by (device, width, height) like the workspaces; a reused array is overwritten.
+static std::vector<PooledTexture> g_texture_pool;
+
+static bool texture_acquire(int device, int w, int h, PooledTexture &out) {
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mutex);
+        for (size_t i = 0; i < g_texture_pool.size(); ++i)
+            if (g_texture_pool[i].device == device && g_texture_pool[i].w == w && g_texture_pool[i].h == h) {
+                out = g_texture_pool[i];
+                g_texture_pool.erase(g_texture_pool.begin() + i);
+                return true;
+            }
+    }
+    out = PooledTexture{device, w, h, nullptr, 0};
+    cudaChannelFormatDesc desc = cudaCreateChannelDesc<uchar4>();
+    if (cudaMallocArray(&out.array, &desc, w, h) != cudaSuccess) return false;
+    cudaResourceDesc res;
+    std::memset(&res, 0, sizeof res);
+    res.resType = cudaResourceTypeArray;
+    res.res.array.array = out.array;
+    cudaTextureDesc td;
+    std::memset(&td, 0, sizeof td);
+    td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModePoint;
+    td.readMode = cudaReadModeElementType;
+    td.normalizedCoords = 0;
+    if (cudaCreateTextureObject(&out.object, &res, &td, nullptr) != cudaSuccess) {
+        cudaFreeArray(out.array);
+        return false;
+    }
+    return true;
+}
+static void texture_release(const PooledTexture &t) {
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    if (g_texture_pool.size() < 16) {
+        g_texture_pool.push_back(t);
+        return;
+    }
+    cudaDestroyTextureObject(t.object);
+    cudaFreeArray(t.array);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // device scene
 // ---------------------------------------------------------------------------------------------------
@@ -87,8 +130,8 @@ void device_scene_free(RtScene *scene) {
     if (!ds) return;
     cudaSetDevice(ds->device);
     if (ds->ws) workspace_release(ds->ws); // synchronises the stream first: nothing is still reading the scene
-    for (auto t : ds->texobjs) cudaDestroyTextureObject(t);
-    for (auto a : ds->arrays) cudaFreeArray(a);
+    for (const PooledTexture &t : ds->images) texture_release(t);
+    cudaFree(ds->ref_nodes);
     cudaFree(ds->blob);
     delete ds;
     scene->dev = nullptr;
@@ -132,29 +175,13 @@ int device_scene_upload(RtScene *scene) {
         if (t.kind == RT_TEX_IMAGE) {
             std::vector<uchar4> texels(size_t(t.width) * t.height);
             for (size_t k = 0; k < texels.size(); ++k) texels[k] = make_uchar4(t.rgb8[3 * k], t.rgb8[3 * k + 1], t.rgb8[3 * k + 2], 255);
-            cudaChannelFormatDesc desc = cudaCreateChannelDesc<uchar4>();
-            cudaArray_t arr = nullptr;
-            if (cudaMallocArray(&arr, &desc, t.width, t.height) != cudaSuccess)
-                return bail(fail(RT_ERR_CUDA, "cudaMallocArray failed for an image texture"));
-            ds->arrays.push_back(arr);
-            if (cudaMemcpy2DToArray(arr, 0, 0, texels.data(), size_t(t.width) * sizeof(uchar4), size_t(t.width) * sizeof(uchar4), t.height,
+            PooledTexture pt;
+            if (!texture_acquire(ds->device, t.width, t.height, pt)) return bail(fail(RT_ERR_CUDA, "texture allocation failed for an image texture"));
+            ds->images.push_back(pt);
+            if (cudaMemcpy2DToArray(pt.array, 0, 0, texels.data(), size_t(t.width) * sizeof(uchar4), size_t(t.width) * sizeof(uchar4), t.height,
                                     cudaMemcpyHostToDevice) != cudaSuccess)
                 return bail(fail(RT_ERR_CUDA, "cudaMemcpy2DToArray failed for an image texture"));
-            cudaResourceDesc res;
-            std::memset(&res, 0, sizeof res);
-            res.resType = cudaResourceTypeArray;
-            res.res.array.array = arr;
-            cudaTextureDesc td;
-            std::memset(&td, 0, sizeof td);
-            td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
-            td.filterMode = cudaFilterModePoint;
-            td.readMode = cudaReadModeElementType;
-            td.normalizedCoords = 0;
-            cudaTextureObject_t obj = 0;
-            if (cudaCreateTextureObject(&obj, &res, &td, nullptr) != cudaSuccess)
-                return bail(fail(RT_ERR_CUDA, "cudaCreateTextureObject failed"));
-            ds->texobjs.push_back(obj);
-            o.tex = obj;
+            o.tex = pt.object;
             ds->bytes += texels.size() * sizeof(uchar4);
         }
     }
@@ -166,7 +193,7 @@ int device_scene_upload(RtScene *scene) {
     const size_t off_mats = align(off_spheres + L.spheres.size() * sizeof(DSphere));
     const size_t off_unb = align(off_mats + L.materials.size() * sizeof(DMaterial));
     const size_t off_ref = align(off_unb + L.unbounded.size() * sizeof(DUnbounded));
-    const size_t off_tex = align(off_ref + L.ref_nodes.size() * sizeof(DRefNode));
+    const size_t off_tex = off_ref;
     const size_t total = align(off_tex + dt.size() * sizeof(DTexture)) + 256;
     std::vector<uint8_t> host(total, 0);
     auto put = [&](size_t off, const void *src, size_t n) {
@@ -176,7 +203,6 @@ int device_scene_upload(RtScene *scene) {
     put(off_spheres, L.spheres.data(), L.spheres.size() * sizeof(DSphere));
     put(off_mats, L.materials.data(), L.materials.size() * sizeof(DMaterial));
     put(off_unb, L.unbounded.data(), L.unbounded.size() * sizeof(DUnbounded));
-    put(off_ref, L.ref_nodes.data(), L.ref_nodes.size() * sizeof(DRefNode));
     put(off_tex, dt.data(), dt.size() * sizeof(DTexture));
     if (cudaMalloc(&ds->blob, total) != cudaSuccess) return bail(fail(RT_ERR_CUDA, "cudaMalloc failed for the scene"));
     if (cudaMemcpy(ds->blob, host.data(), total, cudaMemcpyHostToDevice) != cudaSuccess)
@@ -187,13 +213,24 @@ int device_scene_upload(RtScene *scene) {
     ds->g.spheres = reinterpret_cast<const float4 *>(base + off_spheres);
     ds->g.mats = reinterpret_cast<const uint4 *>(base + off_mats);
     ds->g.unb = reinterpret_cast<const DUnbounded *>(base + off_unb);
-    ds->ref_nodes = reinterpret_cast<DRefNode *>(base + off_ref);
     ds->g.tex = reinterpret_cast<const DTexture *>(base + off_tex);
-    ds->n_ref_nodes = int32_t(L.ref_nodes.size());
     ds->g.n_nodes = int32_t(L.nodes.size());
     ds->g.n_bounded = L.n_bounded;
     ds->g.n_unbounded = int32_t(L.unbounded.size());
     ds->g.n_tex = int32_t(scene->textures.size());
+    return RT_OK;
+}
+
+// uploads the reference-topology tree the first time the conformance traversal asks for it
+int device_scene_ensure_reference(RtScene *scene) {
+    auto *ds = static_cast<DeviceScene *>(scene->dev);
+    if (!ds || ds->ref_nodes) return RT_OK;
+    scene_ensure_reference(scene);
+    const auto &nodes = scene->layout.ref_nodes;
+    RT_CUDA(cudaSetDevice(ds->device));
+    RT_CUDA(cudaMalloc((void **)&ds->ref_nodes, std::max<size_t>(nodes.size(), 1) * sizeof(DRefNode)));
+    if (!nodes.empty()) RT_CUDA(cudaMemcpy(ds->ref_nodes, nodes.data(), nodes.size() * sizeof(DRefNode), cudaMemcpyHostToDevice));
+    ds->n_ref_nodes = int32_t(nodes.size());
     return RT_OK;
 }
 

@@ -57,14 +57,18 @@ struct DeviceWorkspace {
 int workspace_acquire(int device, DeviceWorkspace **out);
 void workspace_release(DeviceWorkspace *ws);
 
+struct PooledTexture { // an image texture's array + texture object, pooled by (device, width, height)
+    int device, w, h;
+    cudaArray_t array;
+    cudaTextureObject_t object;
+};
 struct DeviceScene {
     int device = 0;
     SceneGlobal g{};
     DRefNode *ref_nodes = nullptr;
     int32_t n_ref_nodes = 0;
     void *blob = nullptr; // one allocation holding nodes | spheres | materials | unbounded | reference nodes | textures
-    std::vector<cudaArray_t> arrays;
-    std::vector<cudaTextureObject_t> texobjs;
+    std::vector<PooledTexture> images; // image textures borrowed from the pool
     size_t bytes = 0;
     DeviceWorkspace *ws = nullptr;
 };

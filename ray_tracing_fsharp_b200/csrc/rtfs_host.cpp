@@ -331,8 +331,7 @@ void export_sah(const HostSceneLayout &L, const std::vector<int32_t> &leaf_obj, 
 }
 } // namespace
 
-void build_device_layout(const RtHittable *objs, int32_t n_objs, const std::vector<HostNode> &ref_tree,
-                         HostSceneLayout &L, std::vector<HostNode> &sah_tree_out) {
+void build_device_layout(const RtHittable *objs, int32_t n_objs, HostSceneLayout &L, std::vector<HostNode> &sah_tree_out) {
     L = HostSceneLayout{};
     sah_tree_out.clear();
     SahBuilder b;
@@ -398,17 +397,6 @@ void build_device_layout(const RtHittable *objs, int32_t n_objs, const std::vect
         L.materials.push_back(make_material(h, i));
     }
     L.device_id_of = device_id_of; // bounded spheres with negative radius keep id -1: they can never be returned
-    for (const HostNode &hn : ref_tree) {
-        DRefNode r{};
-        for (int a = 0; a < 3; ++a) {
-            bool inverted = hn.mn[a] > hn.mx[a];
-            r.mn[a] = inverted ? float(hn.mn[a]) : round_down(hn.mn[a]);
-            r.mx[a] = inverted ? float(hn.mx[a]) : round_up(hn.mx[a]);
-        }
-        r.right = hn.right;
-        r.prim = hn.prim >= 0 ? device_id_of[hn.prim] : -1;
-        L.ref_nodes.push_back(r);
-    }
     if (n >= 1) {
         FBox rootb = b.bounds(0, n);
         if (n == 1) {
@@ -416,6 +404,30 @@ void build_device_layout(const RtHittable *objs, int32_t n_objs, const std::vect
         } else {
             export_sah(L, b.leaf_obj, 0, rootb.mn, rootb.mx, sah_tree_out);
         }
+    }
+}
+
+// The reference-topology tree is only needed by the conformance traversal and by inspection; it is built on
+// first use (its median-split build sorts every range three times: half a second for 100 000 spheres).
+void scene_ensure_reference(RtScene *s) {
+    if (s->ref_built) return;
+    s->ref_built = true;
+    std::vector<int32_t> bounded;
+    for (int32_t i = 0; i < int32_t(s->objects.size()); ++i)
+        if (s->objects[i].shape == RT_SHAPE_SPHERE) bounded.push_back(i); // Hittable.BoundingBox, Hittable.fs:14-18
+    build_reference_tree(s->objects.data(), bounded, s->ref_tree);
+    HostSceneLayout &L = s->layout;
+    L.ref_nodes.clear();
+    for (const HostNode &hn : s->ref_tree) {
+        DRefNode r{};
+        for (int a = 0; a < 3; ++a) {
+            bool inverted = hn.mn[a] > hn.mx[a];
+            r.mn[a] = inverted ? float(hn.mn[a]) : round_down(hn.mn[a]);
+            r.mx[a] = inverted ? float(hn.mx[a]) : round_up(hn.mx[a]);
+        }
+        r.right = hn.right;
+        r.prim = hn.prim >= 0 ? L.device_id_of[hn.prim] : -1;
+        L.ref_nodes.push_back(r);
     }
 }
 
@@ -573,11 +585,7 @@ int rt_scene_create(const RtHittable *objects, int32_t n_objects, const RtTextur
             s->textures[t].rgb8 = nullptr;
         }
     }
-    std::vector<int32_t> bounded;
-    for (int32_t i = 0; i < n_objects; ++i)
-        if (objects[i].shape == RT_SHAPE_SPHERE) bounded.push_back(i); // Hittable.BoundingBox, Hittable.fs:14-18
-    build_reference_tree(s->objects.data(), bounded, s->ref_tree);
-    build_device_layout(s->objects.data(), n_objects, s->ref_tree, s->layout, s->sah_tree);
+    build_device_layout(s->objects.data(), n_objects, s->layout, s->sah_tree);
     if (s->layout.max_depth > 60) {
         delete s;
         return fail(RT_ERR_UNSUPPORTED, "rt_scene_create: BVH deeper than the traversal stack");
@@ -602,10 +610,12 @@ void rt_scene_destroy(RtScene *scene) {
 
 int rt_scene_bvh_node_count(const RtScene *scene, int32_t which) {
     if (!scene) return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_bvh_node_count: null scene");
+    if (which == RT_BVH_REFERENCE) scene_ensure_reference(const_cast<RtScene *>(scene));
     return int(which == RT_BVH_REFERENCE ? scene->ref_tree.size() : scene->sah_tree.size());
 }
 int rt_scene_bvh_nodes(const RtScene *scene, int32_t which, double *bounds, int32_t *right, int32_t *prim) {
     if (!scene || !bounds || !right || !prim) return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_bvh_nodes: null argument");
+    if (which == RT_BVH_REFERENCE) scene_ensure_reference(const_cast<RtScene *>(scene));
     const auto &t = which == RT_BVH_REFERENCE ? scene->ref_tree : scene->sah_tree;
     for (size_t i = 0; i < t.size(); ++i) {
         for (int a = 0; a < 3; ++a) {

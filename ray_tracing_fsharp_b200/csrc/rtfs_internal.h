@@ -105,8 +105,7 @@ struct HostSceneLayout {
 // SAH BVH2 over the bounded spheres with radius >= 0 (a bounded sphere with negative radius has an
 // inverted box and is never hit in the reference, F16).  Fills layout.spheres/nodes and the bounded
 // part of layout.materials; also exports the tree in HostNode form for inspection.
-void build_device_layout(const RtHittable *objs, int32_t n_objs, const std::vector<HostNode> &ref_tree,
-                         HostSceneLayout &layout, std::vector<HostNode> &sah_tree_out);
+void build_device_layout(const RtHittable *objs, int32_t n_objs, HostSceneLayout &layout, std::vector<HostNode> &sah_tree_out);
 
 } // namespace rtfs
 
@@ -116,6 +115,7 @@ struct RtScene {
     std::vector<RtTexture> textures;
     std::vector<std::vector<uint8_t>> texture_pixels;
     std::vector<rtfs::HostNode> ref_tree, sah_tree;
+    bool ref_built = false; // the reference-topology tree is built on first use (scene_ensure_reference)
     rtfs::HostSceneLayout layout;
     int32_t device = -1;
     void *dev = nullptr; // rtfs_device.cu: DeviceScene*
@@ -123,7 +123,9 @@ struct RtScene {
 
 // implemented in rtfs_device.cu
 namespace rtfs {
+void scene_ensure_reference(RtScene *scene);
 int device_scene_upload(RtScene *scene);
+int device_scene_ensure_reference(RtScene *scene);
 void device_scene_free(RtScene *scene);
 size_t device_scene_bytes(const RtScene *scene);
 } // namespace rtfs
