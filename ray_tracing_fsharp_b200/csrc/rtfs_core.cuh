@@ -363,11 +363,30 @@ struct TraversalCounters {
 // closest hit does not depend on tree topology or visiting order (only exact ties in t do, F12), so the
 // result equals the reference's exhaustive left-then-right DFS.  Then the unbounded objects in array
 // order, which must win by Float.compare t^2 best^2 = Less (Scene.fs:77-86).
+// One visit of the walk over the tree: `node` is an internal node (>= 0: test both children's boxes, descend into
+// the nearer one, push the other) or a leaf (~k: test sphere k, pop).  Returns true when the walk is over.
 template <bool SMEM, bool COUNT>
-RTFS_HD Hit closest_hit(const SceneAccess<SMEM> &sc, float3 o, float3 d, int last, TraversalCounters &cn, unsigned lanes) {
-    float best_t = kNoHitT;
-    int best = kNoPrim;
-    auto test_leaf = [&](int k) {
+RTFS_HD bool bvh_visit(const SceneAccess<SMEM> &sc, const RaySlabs &rs, float3 o, float3 d, int last, int &node, int &sp, int *stack,
+                       float &best_t, int &best, TraversalCounters &cn) {
+    if (node >= 0) {
+        uint4 q0 = sc.node_q(node, 0), q1 = sc.node_q(node, 1), q2 = sc.node_q(node, 2), q3 = sc.node_q(node, 3);
+        float tl, tr;
+        bool hl = slab_entry(rs, __uint_as_float(q0.x), __uint_as_float(q0.y), __uint_as_float(q0.z), __uint_as_float(q0.w),
+                             __uint_as_float(q1.x), __uint_as_float(q1.y), best_t, tl);
+        bool hr = slab_entry(rs, __uint_as_float(q1.z), __uint_as_float(q1.w), __uint_as_float(q2.x), __uint_as_float(q2.y),
+                             __uint_as_float(q2.z), __uint_as_float(q2.w), best_t, tr);
+        if (COUNT) cn.box_tests += 2;
+        int left = int(q3.x), right = int(q3.y);
+        if (hl && hr) {
+            bool left_first = tl <= tr;
+            stack[sp++] = left_first ? right : left;
+            node = left_first ? left : right;
+            return false;
+        }
+        if (hl) { node = left; return false; }
+        if (hr) { node = right; return false; }
+    } else {
+        int k = ~node;
         float4 s = sc.sphere(k);
         float t;
         if (COUNT) cn.prim_tests += 1;
@@ -375,43 +394,27 @@ RTFS_HD Hit closest_hit(const SceneAccess<SMEM> &sc, float3 o, float3 d, int las
             best_t = t;
             best = k;
         }
-    };
-    if (sc.g.n_bounded > 0) {
-        const RaySlabs rs = make_slabs(o, d);
-        int stack[64];
-        int sp = 0;
-        int node = 0;
-        for (;;) {
-            if (node >= 0) {
-                uint4 q0 = sc.node_q(node, 0), q1 = sc.node_q(node, 1), q2 = sc.node_q(node, 2), q3 = sc.node_q(node, 3);
-                float tl, tr;
-                bool hl = slab_entry(rs, __uint_as_float(q0.x), __uint_as_float(q0.y), __uint_as_float(q0.z),
-                                     __uint_as_float(q0.w), __uint_as_float(q1.x), __uint_as_float(q1.y), best_t, tl);
-                bool hr = slab_entry(rs, __uint_as_float(q1.z), __uint_as_float(q1.w), __uint_as_float(q2.x),
-                                     __uint_as_float(q2.y), __uint_as_float(q2.z), __uint_as_float(q2.w), best_t, tr);
-                if (COUNT) cn.box_tests += 2;
-                int left = int(q3.x), right = int(q3.y);
-                if (hl && hr) {
-                    bool left_first = tl <= tr;
-                    stack[sp++] = left_first ? right : left;
-                    node = left_first ? left : right;
-                    continue;
-                }
-                if (hl) { node = left; continue; }
-                if (hr) { node = right; continue; }
-            } else {
-                test_leaf(~node);
-            }
-            if (sp == 0) break;
-            node = stack[--sp];
-        }
     }
-    // `lanes`: the lanes of this warp that are tracing a ray in this call.  Lanes leave the traversal loop at
-    // different times; make them wait for one another here, so that the unbounded tests and the scatter that
-    // follow run once per warp at full width instead of once per straggler group.
-    // (Tried and dropped: parking a leaf and testing it here, converged, instead of in the loop at ~4 active lanes —
-    // the lost culling costs 5 % more slab tests and the frame got 3 % slower.)
-    converge(lanes);
+    if (sp == 0) return true;
+    node = stack[--sp];
+    return false;
+}
+// the bounded part of hitObject: the closest sphere of the tree, if any
+template <bool SMEM, bool COUNT>
+RTFS_HD void bvh_closest(const SceneAccess<SMEM> &sc, float3 o, float3 d, int last, float &best_t, int &best, TraversalCounters &cn) {
+    best_t = kNoHitT;
+    best = kNoPrim;
+    if (sc.g.n_bounded <= 0) return;
+    const RaySlabs rs = make_slabs(o, d);
+    int stack[64];
+    int sp = 0;
+    int node = 0;
+    while (!bvh_visit<SMEM, COUNT>(sc, rs, o, d, last, node, sp, stack, best_t, best, cn)) {
+    }
+}
+// the unbounded objects, after the tree (Scene.fs:77-86), and the strike point (:91)
+template <bool SMEM, bool COUNT>
+RTFS_HD Hit finish_hit(const SceneAccess<SMEM> &sc, float3 o, float3 d, int last, float best_t, int best, TraversalCounters &cn) {
     if (sc.g.n_unbounded > 0) {
         const D3 od = d3(o), dd = d3(d);
         const double a = dot(dd, dd);
@@ -433,6 +436,19 @@ RTFS_HD Hit closest_hit(const SceneAccess<SMEM> &sc, float3 o, float3 d, int las
     h.prim = best;
     h.strike = fma3(best_t, d, o); // Ray.walkAlong ray bestLength, Scene.fs:91
     return h;
+}
+// `lanes`: the lanes of this warp that are tracing a ray in this call.  They leave the walk at different times and
+// wait for one another before the unbounded tests, so that those and the scatter that follows run once per warp at
+// full width instead of once per straggler group.
+// (Tried and dropped: parking a leaf and testing it after the walk, converged, instead of during it at ~4 active
+// lanes — the lost culling costs 5 % more slab tests and the C2 frame got 3 % slower.)
+template <bool SMEM, bool COUNT>
+RTFS_HD Hit closest_hit(const SceneAccess<SMEM> &sc, float3 o, float3 d, int last, TraversalCounters &cn, unsigned lanes) {
+    float best_t;
+    int best;
+    bvh_closest<SMEM, COUNT>(sc, o, d, last, best_t, best, cn);
+    converge(lanes);
+    return finish_hit<SMEM, COUNT>(sc, o, d, last, best_t, best, cn);
 }
 
 // The reference's own traversal (Scene.fs:30-60, F12): exhaustive left-then-right DFS of the
