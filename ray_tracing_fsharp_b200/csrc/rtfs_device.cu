@@ -255,7 +255,7 @@ __device__ __forceinline__ SceneAccess<SMEM> stage_scene(const FrameParams &fp) 
     return sc;
 }
 
-// per-warp scratch in shared memory: two item slots (one being issued, one whose last paths are still in flight)
+// per-warp scratch in shared memory: item slots (one being issued, the others with their last paths still in flight)
 struct ItemSlot {
     int cursor;    // next path of the item's pool
     int j_begin;   // first local sample index of the item's chunk
@@ -265,8 +265,9 @@ struct ItemSlot {
     int gpix[32];  // row * cols + col of the same pixels, -1: none
     int acc[3][32];
 };
+constexpr int kItemSlots = 4;
 struct WarpScratch {
-    ItemSlot slot[2];
+    ItemSlot slot[kItemSlots];
 };
 static_assert(sizeof(WarpScratch) % 16 == 0, "WarpScratch must be a multiple of 16 bytes");
 
@@ -361,11 +362,13 @@ __global__ void __launch_bounds__(kBlockThreads, 1) render_kernel(const FramePar
 
     unsigned long long item = __shfl_sync(0xffffffffu, fetch_item(), 0);
     if (item < n_items) {
-        // Two slots per warp: lanes pull paths from slot `cur`; when its pool is dry the next item is loaded into the
-        // other slot straight away (as soon as that slot's last in-flight paths have finished and it has been flushed),
-        // so lanes do not idle while the last paths of an item complete.  Only the warp's final item drains.
+        // kItemSlots slots per warp: lanes pull paths from slot `cur`; when its pool is dry the next item is loaded into a
+        // free slot straight away, so lanes do not idle while the last paths of an item complete.  A slot is free once
+        // its in-flight paths have finished and it has been flushed; with long, uneven paths (big scenes) several older
+        // items can have stragglers at once, hence more than two slots.  Only the warp's final items drain.
         int cur = 0;
-        bool other_holds = false, finishing = false;
+        unsigned holds = 1u; // slots that hold an item not yet flushed
+        bool finishing = false;
         int n_entries;
         int pool = load_item(&ws->slot[0], item, n_entries);
         int j_begin = ws->slot[0].j_begin;
@@ -394,21 +397,32 @@ __global__ void __launch_bounds__(kBlockThreads, 1) render_kernel(const FramePar
             // Every lane votes, every iteration: this is where the warp reconverges (lanes that regenerate a path and lanes
             // that do not would otherwise drift apart for good and the traversal would run at a fraction of the warp width).
             if (__any_sync(0xffffffffu, dry)) {
-                // the current pool is exhausted: move on as soon as the other slot is free
-                if (!finishing && !__any_sync(0xffffffffu, active && my != cur)) {
-                    ItemSlot *other = &ws->slot[cur ^ 1];
-                    if (other_holds) flush_item(other);
-                    item = __shfl_sync(0xffffffffu, prefetched, 0);
-                    if (item < n_items) {
-                        pool = load_item(other, item, n_entries);
-                        j_begin = other->j_begin;
-                        prefetched = fetch_item();
-                        cur ^= 1;
-                        other_holds = true; // the slot we just left still has paths in flight
-                        dry = false;
-                    } else {
-                        other_holds = false;
-                        finishing = true;
+                // the current pool is exhausted: retire the older slots whose paths have all finished, then move on
+                if (!finishing) {
+                    int free_slot = -1;
+#pragma unroll
+                    for (int sidx = 0; sidx < kItemSlots; ++sidx) {
+                        if (sidx == cur) continue;
+                        if ((holds >> sidx) & 1u) {
+                            if (__any_sync(0xffffffffu, active && my == sidx)) continue; // stragglers
+                            flush_item(&ws->slot[sidx]);
+                            holds &= ~(1u << sidx);
+                        }
+                        if (free_slot < 0) free_slot = sidx;
+                    }
+                    if (free_slot >= 0) {
+                        item = __shfl_sync(0xffffffffu, prefetched, 0);
+                        if (item < n_items) {
+                            ItemSlot *next = &ws->slot[free_slot];
+                            pool = load_item(next, item, n_entries);
+                            j_begin = next->j_begin;
+                            prefetched = fetch_item();
+                            cur = free_slot;
+                            holds |= 1u << free_slot;
+                            dry = false;
+                        } else {
+                            finishing = true;
+                        }
                     }
                 }
                 if (finishing && !__any_sync(0xffffffffu, active)) break;
@@ -426,7 +440,8 @@ __global__ void __launch_bounds__(kBlockThreads, 1) render_kernel(const FramePar
                 }
             }
         }
-        flush_item(&ws->slot[cur]); // `finishing` was set after the other slot had been flushed
+        for (int sidx = 0; sidx < kItemSlots; ++sidx) // no path is in flight any more
+            if ((holds >> sidx) & 1u) flush_item(&ws->slot[sidx]);
     }
     flush_counters(fp.counters, n_paths, n_rays, cn, COUNT);
 }
