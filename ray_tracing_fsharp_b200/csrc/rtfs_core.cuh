@@ -326,11 +326,31 @@ template <bool SMEM>
 struct SceneAccess {
     SceneGlobal g;
     uint32_t s_nodes, s_spheres, s_mats; // SMEM only: byte addresses of the staged copies in the shared window
-    RTFS_HD uint4 node_q(int i, int q) const {
+    // one 64-byte node: four LDS.128 from the staged copy, or two 256-bit read-only loads from global memory
+    // (sm_100 has LDG.256: half as many L1 requests per divergent node fetch as four 128-bit loads)
+    RTFS_HD void node(int i, uint4 &q0, uint4 &q1, uint4 &q2, uint4 &q3) const {
 #ifdef __CUDACC__
-        if (SMEM) return lds128(s_nodes + 64u * uint32_t(i) + 16u * uint32_t(q));
+        if (SMEM) {
+            const uint32_t a = s_nodes + 64u * uint32_t(i);
+            q0 = lds128(a);
+            q1 = lds128(a + 16u);
+            q2 = lds128(a + 32u);
+            q3 = lds128(a + 48u);
+            return;
+        }
+        const uint4 *p = g.nodes + 4 * i;
+        asm volatile("ld.global.nc.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(q0.x), "=r"(q0.y), "=r"(q0.z), "=r"(q0.w), "=r"(q1.x), "=r"(q1.y), "=r"(q1.z), "=r"(q1.w)
+                     : "l"(p));
+        asm volatile("ld.global.nc.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(q2.x), "=r"(q2.y), "=r"(q2.z), "=r"(q2.w), "=r"(q3.x), "=r"(q3.y), "=r"(q3.z), "=r"(q3.w)
+                     : "l"(p + 2));
+#else
+        q0 = g.nodes[4 * i];
+        q1 = g.nodes[4 * i + 1];
+        q2 = g.nodes[4 * i + 2];
+        q3 = g.nodes[4 * i + 3];
 #endif
-        return __ldg(g.nodes + 4 * i + q);
     }
     RTFS_HD float4 sphere(int i) const {
 #ifdef __CUDACC__
@@ -369,7 +389,8 @@ template <bool SMEM, bool COUNT>
 RTFS_HD bool bvh_visit(const SceneAccess<SMEM> &sc, const RaySlabs &rs, float3 o, float3 d, int last, int &node, int &sp, int *stack,
                        float &best_t, int &best, TraversalCounters &cn) {
     if (node >= 0) {
-        uint4 q0 = sc.node_q(node, 0), q1 = sc.node_q(node, 1), q2 = sc.node_q(node, 2), q3 = sc.node_q(node, 3);
+        uint4 q0, q1, q2, q3;
+        sc.node(node, q0, q1, q2, q3);
         float tl, tr;
         bool hl = slab_entry(rs, __uint_as_float(q0.x), __uint_as_float(q0.y), __uint_as_float(q0.z), __uint_as_float(q0.w),
                              __uint_as_float(q1.x), __uint_as_float(q1.y), best_t, tl);
