@@ -272,3 +272,19 @@ def test_edge_sizes_and_budgets():
     assert int(stats.rays) == int(stats.paths)
     hot = (rgb == np.array([205, 105, 180], np.uint8)).all(2)
     assert hot.any() and not hot.all()
+
+
+@pytest.mark.parametrize("name", ["C1", "C2", "C3", "C4"])
+def test_frames_against_committed_golden_fixtures(name):
+    """tests/golden/oracle_frames.npz: frames the oracle rendered with the shared counter RNG when the fixtures were
+    made (it must still reproduce them bit for bit: test_oracle_reference_kats.py)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_frames.npz"))
+    max_w, max_h, spp = [int(x) for x in g[f"{name}_shape"]]
+    spec = _small(name, max_w, max_h, spp)
+    osc, dsc, cam = scene_pair(spec)
+    rgb, sums, stats = dsc.render(cam, max_w, max_h, seed=2024, adaptive=True, want_sums=True)
+    want_rgb, want_stats = g[f"{name}_rgb"], g[f"{name}_stats"]
+    assert (rgb == want_rgb).all(2).mean() > 0.985
+    assert (sums == want_stats).all(2).mean() > 0.97
+    assert abs(int(stats.paths) - int(g[f"{name}_work"][0])) <= 0.01 * int(g[f"{name}_work"][0])

@@ -234,3 +234,18 @@ def test_product_package_never_touches_the_oracle():
     # and the shared library does not link it
     out = subprocess.check_output(["ldd", native.LIB_PATH], text=True)
     assert "oracle" not in out
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the CPU arm: oracle with all host threads on a bounded sample) — schema check."""
+    import json
+    import sys
+    out = subprocess.check_output([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                                   "--cpu-seconds", "0.5", "--config", "C1"], text=True, timeout=300)
+    lines = [l for l in out.strip().splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "Mrays/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "sample" in d["config"]

@@ -255,3 +255,24 @@ def test_orthonormalise_and_basis_are_orthonormal():
         assert abs(x @ y) < 1e-8 and abs(x @ x - 1) < 1e-8 and abs(y @ y - 1) < 1e-8
         checked += 1
     assert checked > 400
+
+
+# ---- regression fixtures of the oracle itself (tests/golden/make_golden.py) -----------------------------------------
+def _golden_frames():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_frames.npz"))
+
+
+@pytest.mark.parametrize("name", ["C1", "C2", "C3", "C4"])
+def test_oracle_reproduces_its_golden_frames(name):
+    from ray_tracing_fsharp_b200 import sample_images
+    from ray_tracing_fsharp_b200.domain import marshal
+    g = _golden_frames()
+    max_w, max_h, spp = [int(x) for x in g[f"{name}_shape"]]
+    spec = sample_images.CONFIGS[name]()
+    hs, ts, _keep = marshal(spec.objects)
+    cam = oracle.camera_make_basic(spp, spec.focal_length, spec.aspect_ratio, spec.origin, spec.view_direction, spec.view_up)
+    cam.bounce_depth = spec.bounce_depth
+    rgb, stats, counters, _ = oracle.Scene(hs, ts).render(cam, max_w, max_h, seed=2024, rng_mode=1, adaptive=True)
+    assert np.array_equal(rgb, g[f"{name}_rgb"]) and np.array_equal(stats, g[f"{name}_stats"])
+    assert [counters["paths"], counters["rays"]] == g[f"{name}_work"].tolist()
