@@ -83,8 +83,10 @@ def run_reference(args):
     per_step = []
     counters = None
     rows = row_step = 0
+    # every step is a bounded sample of the frame; size it so that the whole run stays within a couple of minutes
+    per_step_seconds = min(args.cpu_seconds, 120.0 / max(1, args.warmup + args.steps))
     for i in range(args.warmup + args.steps):
-        s = cpu_sample(spec, args.cpu_seconds, threads, seed=100 + i)
+        s = cpu_sample(spec, per_step_seconds, threads, seed=100 + i)
         if i >= args.warmup:
             per_step.append(s)
         counters, rows, row_step = s["counters"], s["rows"], s["row_step"]
