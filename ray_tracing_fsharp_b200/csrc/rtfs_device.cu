@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) render_kernel(const FramePar
     auto load_item = [&](ItemSlot *sl, unsigned long long item, int &n_entries) -> int {
         const int k = int(item / n_units);
         const unsigned unit = unsigned(item - (unsigned long long)k * n_units);
-        const int j_begin = fp.chunk_begin[k], j_len = fp.chunk_len[k];
+        const int j_begin = int(fp.chunk_begin[k]), j_len = int(fp.chunk_len[k]);
         int my_pixel = -1;
         n_entries = 32;
         if (PROBE) {
@@ -596,9 +596,9 @@ void fill_frame(FrameParams &fp, DeviceScene *ds, const RtCamera &cam, int max_w
 // bulk/2, bulk/4, ..., 2, 1, 1 so that the last layers of items are short (a warp cannot be sped up, so the
 // kernel ends one item after the work runs out).  No chunk straddles `boundary` (probe: firstTrial + 1, the first
 // sample of the second accumulator set).  Chunks are stored by decreasing length: items are numbered chunk-major.
-static void build_chunks(FrameParams &fp, int n_local, int boundary, size_t n_units, int resident_warps) {
+static int build_chunks(FrameParams &fp, int n_local, int boundary, size_t n_units, int resident_warps) {
     fp.n_chunks = 0;
-    if (n_local <= 0) return;
+    if (n_local <= 0) return RT_OK;
     // bulk chunk: every warp should see ~16 bulk items; at most 32 samples (1024 paths) per item
     long long bulk = (long long)(n_units * size_t(n_local)) / (16LL * std::max(1, resident_warps));
     bulk = std::max(1LL, std::min(32LL, bulk));
@@ -632,11 +632,13 @@ static void build_chunks(FrameParams &fp, int n_local, int boundary, size_t n_un
         at += c;
     }
     std::stable_sort(chunks.begin(), chunks.end(), [](const std::pair<int, int> &a, const std::pair<int, int> &b) { return a.second > b.second; });
-    fp.n_chunks = int(std::min<size_t>(chunks.size(), kMaxChunks));
+    if (chunks.size() > size_t(kMaxChunks)) return fail(RT_ERR_UNSUPPORTED, "render: the sample range needs more chunks than the work table holds");
+    fp.n_chunks = int(chunks.size());
     for (int k = 0; k < fp.n_chunks; ++k) {
-        fp.chunk_begin[k] = uint16_t(chunks[k].first);
-        fp.chunk_len[k] = uint16_t(chunks[k].second);
+        fp.chunk_begin[k] = uint32_t(chunks[k].first);
+        fp.chunk_len[k] = uint32_t(chunks[k].second);
     }
+    return RT_OK;
 }
 
 int launch_probe(DeviceScene *ds, FrameParams fp, bool count, bool no_smem, cudaStream_t st, int *launches) {
@@ -657,7 +659,8 @@ int launch_probe(DeviceScene *ds, FrameParams fp, bool count, bool no_smem, cuda
     int rc = plan_launch(ds, fp, true, count, no_smem, plan, fn);
     if (rc != RT_OK) return rc;
     const size_t n_units = size_t((fp.tiles_x * fp.tiles_y - fp.rank + fp.world - 1) / fp.world);
-    build_chunks(fp, fp.n_probe, fp.first_trial + 1, n_units, plan.blocks * (kBlockThreads / 32));
+    rc = build_chunks(fp, fp.n_probe, fp.first_trial + 1, n_units, plan.blocks * (kBlockThreads / 32));
+    if (rc != RT_OK) return rc;
     fn<<<plan.blocks, kBlockThreads, plan.smem_bytes, st>>>(fp);
     RT_CUDA(cudaGetLastError());
     ++*launches;
@@ -686,7 +689,8 @@ int launch_main(DeviceScene *ds, FrameParams fp, const FlagsView &flags, bool co
     int n_span = fp.sample_end - fp.sample_begin - fp.rank;
     int n_local = n_span > 0 ? (n_span + fp.world - 1) / fp.world : 0;
     // the list length is only known on the device; size the chunks for the whole frame (an upper bound on the units)
-    build_chunks(fp, n_local, -1, (n_pixels + 31) / 32, plan.blocks * (kBlockThreads / 32));
+    rc = build_chunks(fp, n_local, -1, (n_pixels + 31) / 32, plan.blocks * (kBlockThreads / 32));
+    if (rc != RT_OK) return rc;
     if (n_local > 0) {
         fn<<<plan.blocks, kBlockThreads, plan.smem_bytes, st>>>(fp);
         RT_CUDA(cudaGetLastError());

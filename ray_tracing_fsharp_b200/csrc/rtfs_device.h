@@ -92,8 +92,8 @@ struct FrameParams {
     // [chunk_begin[k], chunk_begin[k] + chunk_len[k]); chunks are sorted by decreasing length and items are
     // numbered chunk-major, so the persistent warps meet the long items first and the short ones last
     int32_t n_chunks;
-    uint16_t chunk_begin[kMaxChunks];
-    uint16_t chunk_len[kMaxChunks];
+    uint32_t chunk_begin[kMaxChunks];
+    uint32_t chunk_len[kMaxChunks];
     int32_t *stats;       // rows*cols*4 {sumR, sumG, sumB, count}
     int32_t *stats_b;     // probe phase: sums of the samples after the first firstTrial + 1 (same layout)
     uint8_t *flags;       // rows*cols

@@ -288,3 +288,20 @@ def test_frames_against_committed_golden_fixtures(name):
     assert (rgb == want_rgb).all(2).mean() > 0.985
     assert (sums == want_stats).all(2).mean() > 0.97
     assert abs(int(stats.paths) - int(g[f"{name}_work"][0])) <= 0.01 * int(g[f"{name}_work"][0])
+
+
+def test_large_sample_counts_keep_every_sample():
+    """The work table cuts a rank's samples into chunks; every sample index must be traced exactly once whatever
+    spp is (here a prime well above the table's bulk size, and the 4096 of BASELINE's C5)."""
+    spec = _small("C1", 6, 4, 2999)
+    osc, dsc, cam = scene_pair(spec)
+    for spp in (2999, 4096):
+        cam.samples_per_pixel = spp
+        _, sums, st = dsc.render(cam, 6, 4, seed=5, adaptive=False, want_sums=True)
+        assert (sums[..., 3] == spp).all() and int(st.paths) == spp * sums.shape[0] * sums.shape[1]
+        _, sums_a, st_a = dsc.render(cam, 6, 4, seed=5, adaptive=True, want_sums=True)
+        assert set(np.unique(sums_a[..., 3]).tolist()) <= {11, spp}
+    cam.samples_per_pixel = 2999
+    ref, ref_stats, _, _ = osc.render(cam, 6, 4, seed=5, rng_mode=1, adaptive=False)
+    _, sums, _ = dsc.render(cam, 6, 4, seed=5, adaptive=False, want_sums=True)
+    assert np.abs(sums[..., :3] - ref_stats[..., :3]).max() <= 0.002 * 255 * 2999  # a few paths of 2999 may differ (FP32)
