@@ -305,3 +305,37 @@ def test_large_sample_counts_keep_every_sample():
     ref, ref_stats, _, _ = osc.render(cam, 6, 4, seed=5, rng_mode=1, adaptive=False)
     _, sums, _ = dsc.render(cam, 6, 4, seed=5, adaptive=False, want_sums=True)
     assert np.abs(sums[..., :3] - ref_stats[..., :3]).max() <= 0.002 * 255 * 2999  # a few paths of 2999 may differ (FP32)
+
+
+def test_c1_full_size_4096_spp_against_the_oracle_render():
+    """BASELINE's level-2 bar on configs[0] at its real size (401x225), 4096 spp, adaptive early-out on both sides as
+    the reference renders: the oracle with the reference's xorshift128 generator, the GPU with Philox — independent
+    streams.  Per channel, the mean absolute difference of the pre-gamma means must be under 3 sigma-bar, sigma-bar
+    being the RMS over pixels of the standard error of the difference of two independent estimates (taken from two
+    GPU renders with different seeds); the gamma-corrected P3 bytes are diffed."""
+    spec = sample_images.few_spheres()
+    spec.spp = 4096
+    osc, dsc, cam = scene_pair(spec)
+    mw, mh = spec.max_width_coord, spec.max_height_coord
+    ref, ref_stats, counters, _ = osc.render(cam, mw, mh, seed=1234, rng_mode=0, adaptive=True)
+    a, sa, _ = dsc.render(cam, mw, mh, seed=1, adaptive=True, want_sums=True)
+    b, sb, _ = dsc.render(cam, mw, mh, seed=2, adaptive=True, want_sums=True)
+    mean_a = sa[..., :3] / sa[..., 3:4]
+    mean_b = sb[..., :3] / sb[..., 3:4]
+    mean_o = ref_stats[..., :3] / ref_stats[..., 3:4]
+    var_diff = (mean_a - mean_b) ** 2                       # E = Var(a) + Var(b) = variance of a difference of two estimates
+    sigma_bar = np.sqrt(var_diff.mean(axis=(0, 1)))
+    mad = np.abs(mean_a - mean_o).mean(axis=(0, 1))
+    assert (mad < 3.0 * sigma_bar + 0.25).all(), (mad, sigma_bar)
+    # and the two GPU renders are as far from each other as each is from the oracle (same distribution)
+    mad_gpu = np.abs(mean_a - mean_b).mean(axis=(0, 1))
+    assert (mad < 1.5 * mad_gpu + 0.25).all(), (mad, mad_gpu)
+    # early-out behaves alike: the fraction of pixels that stop after 11 samples
+    frac_o, frac_g = (ref_stats[..., 3] == 11).mean(), (sa[..., 3] == 11).mean()
+    assert abs(frac_o - frac_g) < 0.02, (frac_o, frac_g)
+    # P3 bytes (gamma-corrected), GPU writer vs oracle writer
+    ppm_g = np.array(ImageOutput.write_ppm(True, a).split()[4:], dtype=np.int32)
+    ppm_o = np.array(oracle.ppm_format(ref, True).split()[4:], dtype=np.int32)
+    diff = np.abs(ppm_g - ppm_o)
+    assert diff.size == 3 * 401 * 225
+    assert np.mean(diff <= 2) > 0.9 and np.mean(diff) < 1.5, (np.mean(diff <= 2), np.mean(diff), np.percentile(diff, 99))
