@@ -28,6 +28,7 @@ constexpr float kTolF = 1e-8f;   // Float.tolerance, RayTracing/Float.fs:80
 constexpr double kTolD = 1e-8;
 constexpr uint32_t kWhite = 0x00FFFFFFu, kBlack = 0u, kHotPink = (205u << 16) | (105u << 8) | 180u; // Pixel.fs:18-66
 constexpr int kNoPrim = -1;
+constexpr int kNoRef = 0x7fffffff; // "no primitive" where primitives are named by ref (see SceneAccess)
 constexpr float kNoHitT = 3.402823466e38f; // "bestFloat = infinity" (Scene.fs:65) as the largest finite float
 
 // reconvergence point for the given lanes of the warp (no-op in the host-compiled debug build)
@@ -210,6 +211,18 @@ RTFS_HD bool slab_entry(const RaySlabs &r, float mnx, float mny, float mnz, floa
     return t_near <= fminf(t_far, best_t);
 }
 
+// sqrt for an argument known to be a normal number: one MUFU.SQRT (2 ulp) instead of the ten-instruction IEEE
+// sequence; the hit distance only has to hold 1e-5 relative
+RTFS_HD float sqrt_fast(float x) {
+#ifdef __CUDA_ARCH__
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return sqrtf(x);
+#endif
+}
+
 // ---- Sphere.firstIntersection (Sphere.fs:349-386) -------------------------------------------------------
 // FP32 form for the bounded spheres.  The discriminant is evaluated as r^2 - |oc - b d|^2 (Haines et al.,
 // "Precision Improvements for Ray/Sphere Intersection"), algebraically the reference's b^2 - (|oc|^2 - r^2)
@@ -230,7 +243,7 @@ RTFS_HD bool sphere_hit(float3 o, float3 d, float4 s, bool self, float &t_out) {
     } else if (disc < 0.0f) {
         return false;
     } else {
-        float im = sqrtf(disc);
+        float im = sqrt_fast(disc); // disc >= 1e-8 here
         float i1 = im - b, i2 = -(b + im);
         bool p1 = i1 > kTolF, p2 = i2 > kTolF;
         if (p1 && p2)
@@ -328,10 +341,18 @@ struct SceneAccess {
     uint32_t s_nodes, s_spheres, s_mats; // SMEM only: byte addresses of the staged copies in the shared window
     // one 64-byte node: four LDS.128 from the staged copy, or two 256-bit read-only loads from global memory
     // (sm_100 has LDG.256: half as many L1 requests per divergent node fetch as four 128-bit loads)
+    // Child references.  A walk holds a `ref`: >= 0 an internal node, < 0 a leaf.  Read from global memory a ref is
+    // the node index / ~sphere index the host wrote.  In the staged copy (SMEM) stage_tree() has rewritten every
+    // ref into the shared-window byte address of what it points at (node: address; leaf: ~address of the sphere), so
+    // a visit needs no address arithmetic at all (the compiler would otherwise rebuild base + 64 i from special
+    // registers on every visit rather than keep the base in a register).
+    RTFS_HD int root() const { return SMEM ? int(s_nodes) : 0; }
+    RTFS_HD int ref_of_sphere(int k) const { return SMEM ? ~int(s_spheres + 16u * uint32_t(k)) : ~k; }
+    RTFS_HD int sphere_of_ref(int ref) const { return SMEM ? int((uint32_t(~ref) - s_spheres) >> 4) : ~ref; }
     RTFS_HD void node(int i, uint4 &q0, uint4 &q1, uint4 &q2, uint4 &q3) const {
 #ifdef __CUDACC__
         if (SMEM) {
-            const uint32_t a = s_nodes + 64u * uint32_t(i);
+            const uint32_t a = uint32_t(i);
             q0 = lds128(a);
             q1 = lds128(a + 16u);
             q2 = lds128(a + 32u);
@@ -352,6 +373,33 @@ struct SceneAccess {
         q3 = g.nodes[4 * i + 3];
 #endif
     }
+    RTFS_HD float4 sphere_at(int ref) const { // the sphere a leaf ref points at
+#ifdef __CUDACC__
+        if (SMEM) {
+            uint4 v = lds128(uint32_t(~ref));
+            return make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
+        }
+#endif
+        return __ldg(g.spheres + ~ref);
+    }
+#ifdef __CUDACC__
+    // Copies the whole scene (SMEM) into shared memory at s_nodes / s_spheres / s_mats, rewriting the child refs
+    // of the nodes (see above).  Every thread of the block must call it; ends in __syncthreads().
+    __device__ __forceinline__ void stage_tree(uint32_t q_nodes, uint32_t q_spheres, uint32_t q_mats) const {
+        const int n_nodes_q = g.n_nodes * 4, n_sph_q = g.n_bounded, n_mat_q = (g.n_bounded + g.n_unbounded) * 2;
+        for (int i = threadIdx.x; i < n_nodes_q; i += blockDim.x) {
+            uint4 v = __ldg(g.nodes + i);
+            if ((i & 3) == 3) { // {left, right, -, -}
+                v.x = int(v.x) >= 0 ? s_nodes + 64u * v.x : uint32_t(ref_of_sphere(~int(v.x)));
+                v.y = int(v.y) >= 0 ? s_nodes + 64u * v.y : uint32_t(ref_of_sphere(~int(v.y)));
+            }
+            rtfs_smem[q_nodes + i] = v;
+        }
+        for (int i = threadIdx.x; i < n_sph_q; i += blockDim.x) rtfs_smem[q_spheres + i] = __ldg(reinterpret_cast<const uint4 *>(g.spheres) + i);
+        for (int i = threadIdx.x; i < n_mat_q; i += blockDim.x) rtfs_smem[q_mats + i] = __ldg(g.mats + i);
+        __syncthreads();
+    }
+#endif
     RTFS_HD float4 sphere(int i) const {
 #ifdef __CUDACC__
         if (SMEM) {
@@ -372,6 +420,7 @@ struct SceneAccess {
 struct Hit {
     float t;
     int32_t prim; // device primitive id, kNoPrim: nothing hit
+    int32_t ref;  // the same primitive as a walk names it: leaf ref (bounded sphere) | device id (unbounded) | kNoRef
     float3 strike;
 };
 
@@ -385,8 +434,9 @@ struct TraversalCounters {
 // order, which must win by Float.compare t^2 best^2 = Less (Scene.fs:77-86).
 // One visit of the walk over the tree: `node` is an internal node (>= 0: test both children's boxes, descend into
 // the nearer one, push the other) or a leaf (~k: test sphere k, pop).  Returns true when the walk is over.
+// `node`, `last_ref`, `best` and the stack entries are refs (SceneAccess); best >= 0 (kNoRef): nothing hit yet.
 template <bool SMEM, bool COUNT>
-RTFS_HD bool bvh_visit(const SceneAccess<SMEM> &sc, const RaySlabs &rs, float3 o, float3 d, int last, int &node, int &sp, int *stack,
+RTFS_HD bool bvh_visit(const SceneAccess<SMEM> &sc, const RaySlabs &rs, float3 o, float3 d, int last_ref, int &node, int &sp, int *stack,
                        float &best_t, int &best, TraversalCounters &cn) {
     if (node >= 0) {
         uint4 q0, q1, q2, q3;
@@ -407,35 +457,43 @@ RTFS_HD bool bvh_visit(const SceneAccess<SMEM> &sc, const RaySlabs &rs, float3 o
         if (hl) { node = left; return false; }
         if (hr) { node = right; return false; }
     } else {
-        int k = ~node;
-        float4 s = sc.sphere(k);
+        float4 s = sc.sphere_at(node);
         float t;
         if (COUNT) cn.prim_tests += 1;
-        if (sphere_hit(o, d, s, k == last, t) && t < best_t) {
+        if (sphere_hit(o, d, s, node == last_ref, t) && t < best_t) {
             best_t = t;
-            best = k;
+            best = node;
         }
     }
     if (sp == 0) return true;
     node = stack[--sp];
     return false;
 }
+// A path remembers the primitive its ray leaves as the walk names it: the leaf ref of a bounded sphere (< 0), the
+// device id of an unbounded object (>= n_bounded), kNoRef for a camera ray.  From a device primitive id:
+template <bool SMEM>
+RTFS_HD int ref_of_prim(const SceneAccess<SMEM> &sc, int prim) {
+    return prim < 0 ? kNoRef : (prim < sc.g.n_bounded ? sc.ref_of_sphere(prim) : prim);
+}
 // the bounded part of hitObject: the closest sphere of the tree, if any
 template <bool SMEM, bool COUNT>
-RTFS_HD void bvh_closest(const SceneAccess<SMEM> &sc, float3 o, float3 d, int last, float &best_t, int &best, TraversalCounters &cn) {
+RTFS_HD void bvh_closest(const SceneAccess<SMEM> &sc, float3 o, float3 d, int last_ref, float &best_t, int &best_ref, TraversalCounters &cn) {
     best_t = kNoHitT;
-    best = kNoPrim;
+    best_ref = kNoRef;
     if (sc.g.n_bounded <= 0) return;
     const RaySlabs rs = make_slabs(o, d);
     int stack[64];
     int sp = 0;
-    int node = 0;
-    while (!bvh_visit<SMEM, COUNT>(sc, rs, o, d, last, node, sp, stack, best_t, best, cn)) {
+    int node = sc.root();
+    while (!bvh_visit<SMEM, COUNT>(sc, rs, o, d, last_ref, node, sp, stack, best_t, best_ref, cn)) {
     }
 }
 // the unbounded objects, after the tree (Scene.fs:77-86), and the strike point (:91)
+// (`last_ref` and `best_ref` are refs; an unbounded object's ref is its device id)
 template <bool SMEM, bool COUNT>
-RTFS_HD Hit finish_hit(const SceneAccess<SMEM> &sc, float3 o, float3 d, int last, float best_t, int best, TraversalCounters &cn) {
+RTFS_HD Hit finish_hit(const SceneAccess<SMEM> &sc, float3 o, float3 d, int last_ref, float best_t, int best_ref, TraversalCounters &cn) {
+    const int last = last_ref;
+    int best = best_ref;
     if (sc.g.n_unbounded > 0) {
         const D3 od = d3(o), dd = d3(d);
         const double a = dot(dd, dd);
@@ -454,7 +512,8 @@ RTFS_HD Hit finish_hit(const SceneAccess<SMEM> &sc, float3 o, float3 d, int last
     }
     Hit h;
     h.t = best_t;
-    h.prim = best;
+    h.ref = best;
+    h.prim = best < 0 ? sc.sphere_of_ref(best) : (best == kNoRef ? kNoPrim : best);
     h.strike = fma3(best_t, d, o); // Ray.walkAlong ray bestLength, Scene.fs:91
     return h;
 }
@@ -464,12 +523,17 @@ RTFS_HD Hit finish_hit(const SceneAccess<SMEM> &sc, float3 o, float3 d, int last
 // (Tried and dropped: parking a leaf and testing it after the walk, converged, instead of during it at ~4 active
 // lanes — the lost culling costs 5 % more slab tests and the C2 frame got 3 % slower.)
 template <bool SMEM, bool COUNT>
-RTFS_HD Hit closest_hit(const SceneAccess<SMEM> &sc, float3 o, float3 d, int last, TraversalCounters &cn, unsigned lanes) {
+RTFS_HD Hit closest_hit_from(const SceneAccess<SMEM> &sc, float3 o, float3 d, int last_ref, TraversalCounters &cn, unsigned lanes) {
     float best_t;
-    int best;
-    bvh_closest<SMEM, COUNT>(sc, o, d, last, best_t, best, cn);
+    int best_ref;
+    bvh_closest<SMEM, COUNT>(sc, o, d, last_ref, best_t, best_ref, cn);
     converge(lanes);
-    return finish_hit<SMEM, COUNT>(sc, o, d, last, best_t, best, cn);
+    return finish_hit<SMEM, COUNT>(sc, o, d, last_ref, best_t, best_ref, cn);
+}
+// the same with the ray's previous primitive given as a device primitive id (conformance entry points, wavefront)
+template <bool SMEM, bool COUNT>
+RTFS_HD Hit closest_hit(const SceneAccess<SMEM> &sc, float3 o, float3 d, int last, TraversalCounters &cn, unsigned lanes) {
+    return closest_hit_from<SMEM, COUNT>(sc, o, d, ref_of_prim(sc, last), cn, lanes);
 }
 
 // The reference's own traversal (Scene.fs:30-60, F12): exhaustive left-then-right DFS of the
@@ -521,6 +585,7 @@ RTFS_HD Hit closest_hit_reference(const DRefNode *ref_nodes, int n_ref_nodes, co
     Hit h;
     h.t = best_t;
     h.prim = best;
+    h.ref = kNoRef; // not used by the callers of the conformance traversal
     h.strike = fma3(best_t, d, o);
     return h;
 }
@@ -724,7 +789,7 @@ RTFS_HD ScatterResult scatter(const SceneAccess<SMEM> &sc, int prim, int last, f
 struct PathState {
     float3 o, d;
     uint32_t colour;
-    int32_t last;
+    int32_t last; // the primitive the ray leaves, as a ref (see ref_of_prim)
     int32_t bounces;
     CounterRng rng;
 };
@@ -737,23 +802,23 @@ RTFS_HD bool path_begin(PathState &p, const DevCamera &cam, uint32_t k0, uint32_
     p.rng.retry = 0;
     float4 u = p.rng.next(); // rand.GetTwo (), Scene.fs:129
     p.colour = kWhite;
-    p.last = kNoPrim;
+    p.last = kNoRef;
     p.bounces = 0;
     int row = cam.max_h - row_idx - 1; // Scene.fs:219
     int col = col_idx - cam.max_w;     // Scene.fs:226
     return camera_ray(cam, row, col, u.x, u.y, p.o, p.d);
 }
-// returns true when the path is finished; `result` is then its Pixel
-template <bool SMEM, bool COUNT>
-RTFS_HD bool path_step(PathState &p, const SceneAccess<SMEM> &sc, int max_count, uint32_t &result, TraversalCounters &cn, unsigned lanes) {
-    Hit h = closest_hit<SMEM, COUNT>(sc, p.o, p.d, p.last, cn, lanes);
+// the part of a step that follows hitObject: Reflection, bounce count (Scene.fs:102-114).
+// Returns true when the path is finished; `result` is then its Pixel.
+template <bool SMEM>
+RTFS_HD bool path_after_hit(PathState &p, const SceneAccess<SMEM> &sc, const Hit &h, int max_count, uint32_t &result) {
     if (h.prim == kNoPrim) { // the ray goes off into the distance
         result = kBlack;
         return true;
     }
     p.rng.bounce = uint32_t(p.bounces + 1);
     p.rng.retry = 0;
-    ScatterResult r = scatter(sc, h.prim, p.last, p.o, p.d, h.strike, p.colour, p.rng, (bool *)nullptr);
+    ScatterResult r = scatter(sc, h.prim, h.ref == p.last ? h.prim : kNoPrim, p.o, p.d, h.strike, p.colour, p.rng, (bool *)nullptr);
     if (r == SCATTER_ABSORBED) {
         result = p.colour;
         return true;
@@ -762,13 +827,19 @@ RTFS_HD bool path_step(PathState &p, const SceneAccess<SMEM> &sc, int max_count,
         result = kBlack;
         return true;
     }
-    p.last = h.prim;
+    p.last = h.ref;
     p.bounces += 1;
     if (p.bounces > max_count) { // while bounces <= maxCount, Scene.fs:98; not done => HotPink :114
         result = kHotPink;
         return true;
     }
     return false;
+}
+// one whole step: hitObject + Reflection; returns true when the path is finished
+template <bool SMEM, bool COUNT>
+RTFS_HD bool path_step(PathState &p, const SceneAccess<SMEM> &sc, int max_count, uint32_t &result, TraversalCounters &cn, unsigned lanes) {
+    Hit h = closest_hit_from<SMEM, COUNT>(sc, p.o, p.d, p.last, cn, lanes);
+    return path_after_hit<SMEM>(p, sc, h, max_count, result);
 }
 
 } // namespace rtfs

@@ -246,11 +246,7 @@ __device__ __forceinline__ SceneAccess<SMEM> stage_scene(const FrameParams &fp) 
     sc.s_spheres = window + 16u * fp.s_spheres;
     sc.s_mats = window + 16u * fp.s_mats;
     if (SMEM) {
-        const int n_nodes_q = fp.g.n_nodes * 4, n_sph_q = fp.g.n_bounded, n_mat_q = (fp.g.n_bounded + fp.g.n_unbounded) * 2;
-        for (int i = threadIdx.x; i < n_nodes_q; i += blockDim.x) rtfs_smem[fp.s_nodes + i] = __ldg(fp.g.nodes + i);
-        for (int i = threadIdx.x; i < n_sph_q; i += blockDim.x) rtfs_smem[fp.s_spheres + i] = __ldg(reinterpret_cast<const uint4 *>(fp.g.spheres) + i);
-        for (int i = threadIdx.x; i < n_mat_q; i += blockDim.x) rtfs_smem[fp.s_mats + i] = __ldg(fp.g.mats + i);
-        __syncthreads();
+        sc.stage_tree(fp.s_nodes, fp.s_spheres, fp.s_mats);
     }
     return sc;
 }
@@ -432,7 +428,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) render_kernel(const FramePar
                 uint32_t result;
                 ++n_rays;
                 if (path_step<SMEM, COUNT>(ps, sc, fp.cam.depth, result, cn, tracing)) {
-                    int *acc = &ws->slot[my].acc[0][0];
+                    int *acc = &ws->slot[my].acc[0][0]; // PixelStats.add into the item's accumulators
                     atomicAdd(acc + lane_slot, int((result >> 16) & 255u));
                     atomicAdd(acc + 32 + lane_slot, int((result >> 8) & 255u));
                     atomicAdd(acc + 64 + lane_slot, int(result & 255u));

@@ -60,13 +60,7 @@ __device__ __forceinline__ SceneAccess<SMEM> wf_stage(const WfParams &p) {
     sc.s_nodes = window + 16u * p.s_nodes;
     sc.s_spheres = window + 16u * p.s_spheres;
     sc.s_mats = window + 16u * p.s_mats;
-    if (SMEM) {
-        const int n_nodes_q = p.g.n_nodes * 4, n_sph_q = p.g.n_bounded, n_mat_q = (p.g.n_bounded + p.g.n_unbounded) * 2;
-        for (int i = threadIdx.x; i < n_nodes_q; i += blockDim.x) rtfs_smem[p.s_nodes + i] = __ldg(p.g.nodes + i);
-        for (int i = threadIdx.x; i < n_sph_q; i += blockDim.x) rtfs_smem[p.s_spheres + i] = __ldg(reinterpret_cast<const uint4 *>(p.g.spheres) + i);
-        for (int i = threadIdx.x; i < n_mat_q; i += blockDim.x) rtfs_smem[p.s_mats + i] = __ldg(p.g.mats + i);
-        __syncthreads();
-    }
+    if (SMEM) sc.stage_tree(p.s_nodes, p.s_spheres, p.s_mats);
     return sc;
 }
 
