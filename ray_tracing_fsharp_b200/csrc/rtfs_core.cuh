@@ -154,6 +154,27 @@ RTFS_HD bool camera_ray(const DevCamera &c, int row, int col, float r1, float r2
     return unitise(v, d);
 }
 
+// sqrt for an argument known to be a normal number: one MUFU.SQRT (2 ulp) instead of the ten-instruction IEEE
+// sequence; the hit distance only has to hold 1e-5 relative
+RTFS_HD float rcp_fast(float x) { // 1 / x for |x| in the normal range: one MUFU.RCP (1 ulp), no denormal rescaling
+#ifdef __CUDA_ARCH__
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / x;
+#endif
+}
+RTFS_HD float sqrt_fast(float x) {
+#ifdef __CUDA_ARCH__
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return sqrtf(x);
+#endif
+}
+
 // ---- BoundingBox.hits with inverseDirections (BoundingBox.fs:25-94) -----------------------------------
 // Decision-exact restatement: same comparison order, same +-inf / NaN behaviour (a NaN from 0 * inf
 // fails every comparison and so leaves tMin / tMax unchanged).  No early return is needed: the bail-outs
@@ -196,7 +217,7 @@ RTFS_HD RaySlabs make_slabs(float3 o, float3 d) {
     float z = fabsf(d.z) < tiny ? copysignf(tiny, d.z) : d.z;
     RaySlabs r;
     // approximate reciprocals (1 ulp): the slab test is padded, and noi is built from the same inv
-    r.inv = f3(__fdividef(1.0f, x), __fdividef(1.0f, y), __fdividef(1.0f, z));
+    r.inv = f3(rcp_fast(x), rcp_fast(y), rcp_fast(z)); // |x|, |y|, |z| >= 1e-30: normal numbers
     r.noi = f3(-o.x * r.inv.x, -o.y * r.inv.y, -o.z * r.inv.z);
     r.pad = 4.8e-7f * fmaxf(fmaxf(fabsf(r.noi.x), fabsf(r.noi.y)), fabsf(r.noi.z));
     return r;
@@ -209,18 +230,6 @@ RTFS_HD bool slab_entry(const RaySlabs &r, float mnx, float mny, float mnz, floa
     float t_far = fmaf(fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)), 1.0000003576278687f, r.pad);
     entry = t_near;
     return t_near <= fminf(t_far, best_t);
-}
-
-// sqrt for an argument known to be a normal number: one MUFU.SQRT (2 ulp) instead of the ten-instruction IEEE
-// sequence; the hit distance only has to hold 1e-5 relative
-RTFS_HD float sqrt_fast(float x) {
-#ifdef __CUDA_ARCH__
-    float r;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-#else
-    return sqrtf(x);
-#endif
 }
 
 // ---- Sphere.firstIntersection (Sphere.fs:349-386) -------------------------------------------------------
