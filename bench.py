@@ -31,6 +31,16 @@ def flops_per_ray(c):
     return 3.0 + 12.0 * c["box_tests"] / rays + 20.0 * c["sphere_tests"] / rays + 14.0 * c["plane_tests"] / rays + c["candidates"] / rays + 6.0
 
 
+# the same figure per config, measured by the oracle; used when the CPU sample does not run (N > 1)
+FLOPS_PER_RAY = {"C1": 96.0, "C2": 414.0, "C3": 75.0, "C4": 131.0, "C5": 1927.0}
+
+
+def metric_name(spec, config):
+    if config == "C2":
+        return "Mrays/s, RTOW final scene 1201x801 500spp depth 50 (Mpaths/s alongside)"
+    return f"Mrays/s, {spec.name}, {spec.cols}x{spec.rows} {spec.spp}spp depth {spec.bounce_depth} (Mpaths/s alongside)"
+
+
 def build_spec(args):
     from ray_tracing_fsharp_b200 import sample_images
     fn = sample_images.CONFIGS[args.config]
@@ -58,14 +68,18 @@ def cpu_sample(spec, target_seconds, threads, seed=7):
     scene = oracle.Scene(hs, ts)
     cam = oracle.camera_make_basic(spec.spp, spec.focal_length, spec.aspect_ratio, spec.origin, spec.view_direction, spec.view_up)
     cam.bounce_depth = spec.bounce_depth
-    # calibrate on a few rows spread over the frame
+    # calibrate on a few rows spread over the frame, at no more than 64 spp (a row of the 100 k-sphere frame at 4096 spp
+    # takes the host cores 20 s); the time of a row is at most linear in spp beyond that
     step0 = max(1, spec.rows // 8)
+    spp_cal = min(spec.spp, 64)
+    cam_cal = oracle.camera_make_basic(spp_cal, spec.focal_length, spec.aspect_ratio, spec.origin, spec.view_direction, spec.view_up)
+    cam_cal.bounce_depth = spec.bounce_depth
     t0 = time.perf_counter()
-    _, _, c0, rows0 = scene.render(cam, spec.max_width_coord, spec.max_height_coord, seed=seed, rng_mode=0, adaptive=True, threads=threads,
+    _, _, c0, rows0 = scene.render(cam_cal, spec.max_width_coord, spec.max_height_coord, seed=seed, rng_mode=0, adaptive=True, threads=threads,
                                    row_begin=step0 // 2, row_step=step0)
     dt0 = time.perf_counter() - t0
-    per_row = dt0 / max(1, rows0)
-    n_rows = int(min(spec.rows, max(rows0, target_seconds / max(per_row, 1e-9))))
+    per_row = dt0 / max(1, rows0) * (spec.spp / spp_cal)
+    n_rows = int(min(spec.rows, max(1, target_seconds / max(per_row, 1e-9))))
     row_step = max(1, spec.rows // max(1, n_rows))
     t0 = time.perf_counter()
     _, _, c, rows = scene.render(cam, spec.max_width_coord, spec.max_height_coord, seed=seed + 1, rng_mode=0, adaptive=True, threads=threads,
@@ -97,7 +111,8 @@ def run_reference(args):
     sample = f"every {row_step}th row of the frame ({rows} of {spec.rows} rows) at full spp per step"
     line = {
         "impl": "reference",
-        "metric": "Mrays/s, RTOW final scene 1201x801 500spp (C++ restatement of the F# CPU renderer; .NET is absent from this image)",
+        "metric": metric_name(spec, args.config),
+        "note": "CPU arm = the oracle, a C++ restatement of the F# CPU renderer, row-parallel on all host threads (.NET is absent from this image)",
         "value": mrays, "unit": "Mrays/s", "mpaths_per_s": paths / secs / 1e6,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, len(per_step)),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -330,17 +345,17 @@ def run_ours(args):
                    "mpaths_per_s": s["counters"]["paths"] / s["seconds"] / 1e6, "counters": s["counters"]}
         # algorithmic FLOPs per ray of the REFERENCE traversal on this scene: measured by the oracle on the CPU
         # sample when it ran, else the figure recorded in DESIGN.md for C2
-        f_ray = flops_per_ray(cpu["counters"]) if cpu else args.flops_per_ray
+        f_ray = flops_per_ray(cpu["counters"]) if cpu else (args.flops_per_ray or FLOPS_PER_RAY[args.config])
         achieved = main_rays_rank0 / (main_ms / 1e3) * f_ray / 1e12
         traffic = None
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-        if os.path.exists(tp):
+        if os.path.exists(tp) and args.config == "C2" and not args.spp and not args.half_extents:  # the ncu capture is of the C2 main kernel
             try:
                 traffic = json.load(open(tp)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
         line = {
-            "metric": "Mrays/s, RTOW final scene 1201x801 500spp depth 50 (Mpaths/s alongside)",
+            "metric": metric_name(spec, args.config),
             "value": value, "unit": "Mrays/s", "mpaths_per_s": paths / secs / 1e6,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -383,8 +398,8 @@ def main():
     ap.add_argument("--no-smem", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--counters", action="store_true", help="also report box / primitive tests per ray of the device traversal")
-    ap.add_argument("--cpu-seconds", type=float, default=15.0)
-    ap.add_argument("--flops-per-ray", type=float, default=414.0, help="FLOPs of the reference traversal per ray on C2 (DESIGN.md); used when the CPU sample does not run")
+    ap.add_argument("--cpu-seconds", type=float, default=25.0)
+    ap.add_argument("--flops-per-ray", type=float, default=0.0, help="FLOPs of the reference traversal per ray, used when the CPU sample does not run (default: the config's figure from DESIGN.md)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

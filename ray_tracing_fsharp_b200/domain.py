@@ -13,6 +13,7 @@ Reference types mirrored:
   InfinitePlaneStyle, InfinitePlane RayTracing/InfinitePlane.fs:3-13, :101-119
   Hittable                          RayTracing/Hittable.fs:3-6
 """
+import math
 from dataclasses import dataclass, field
 from typing import Any, List, Optional, Sequence, Tuple
 
@@ -75,6 +76,54 @@ class ParameterisedTexture:
     class Image:
         """`Pixel[][]` as ParameterisedTexture.Image holds it: img[y][x], uint8 array [H, W, 3]."""
         img: np.ndarray
+
+    @dataclass(frozen=True, eq=False)
+    class Arbitrary:
+        """ParameterisedTexture.Arbitrary of (float -> float -> Texture) (Texture.fs:24): a host closure of the
+        surface coordinates (u, v) in [0, 1]^2.  It cannot cross the ABI; `bake` samples it into an Image."""
+        f: Any
+
+    @staticmethod
+    def bake(texture, interpret: PlaneMapInverse, width: int = 1024, height: int = 512) -> "ParameterisedTexture.Image":
+        """Samples a ParameterisedTexture (typically an Arbitrary closure) into a `width` x `height` Image that
+        the device can look up.  Texel (x, y) of an Image answers the lookups with
+        int((1 - u)(W - 1)) = x and int(v (H - 1)) = y (Texture.fs:63-67); it is given the closure's value at
+        the centre of that cell.  An approximation by construction (a closure with detail finer than a texel
+        is smoothed to the texel grid), hence explicit: Scene.make never bakes on its own."""
+        if width < 2 or height < 2:
+            raise ValueError("bake: width and height must be at least 2")
+        img = np.empty((height, width, 3), np.uint8)
+        for y in range(height):
+            v = min(1.0, (y + 0.5) / (height - 1))
+            for x in range(width):
+                u = max(0.0, 1.0 - (x + 0.5) / (width - 1))
+                img[y, x] = ParameterisedTexture.colour_at(interpret, texture, u, v).as_tuple()
+        return ParameterisedTexture.Image(img)
+
+    @staticmethod
+    def colour_at(interpret: PlaneMapInverse, t, u: float, v: float) -> Pixel:
+        """ParameterisedTexture.colourAt (Texture.fs:50-67) at surface coordinates (u, v), on the host."""
+        if isinstance(t, ParameterisedTexture.Colour):
+            return t.pixel
+        if isinstance(t, ParameterisedTexture.Arbitrary):
+            r = t.f(u, v)
+            if isinstance(r, Pixel):
+                return r
+            if isinstance(r, Texture.Colour):
+                return r.pixel
+            if isinstance(r, Texture.Arbitrary):  # Texture.colourAt p (f x y): the closure wants the point itself
+                return r.f(Sphere.plane_map(interpret.radius, interpret.centre, u, v))
+            raise TypeError("ParameterisedTexture.Arbitrary must return a Texture")
+        if isinstance(t, ParameterisedTexture.Checkered):
+            sine = math.sin(t.grid_size * u) * math.sin(t.grid_size * v)
+            less = abs(sine) >= 1e-8 and sine < 0.0  # Float.compare sine 0.0 = Less (Float.fs:88-96)
+            return ParameterisedTexture.colour_at(interpret, t.even if less else t.odd, u, v)
+        if isinstance(t, ParameterisedTexture.Image):
+            h, w = t.img.shape[0], t.img.shape[1]
+            x = int((1.0 - u) * float(w - 1))
+            y = int(v * float(h - 1))
+            return Pixel(*[int(c) for c in t.img[y, x]])
+        raise TypeError(f"not a ParameterisedTexture: {t!r}")
 
     @staticmethod
     def of_image(bitmap: np.ndarray) -> "ParameterisedTexture.Image":
@@ -171,6 +220,14 @@ class Sphere:
         return Sphere(style, c, float(radius))
 
     @staticmethod
+    def plane_map(radius, centre, phi: float, theta: float) -> Tuple[float, float, float]:
+        """Sphere.planeMap (Sphere.fs:46-52): the point of the sphere at surface coordinates (phi, theta) in [0, 1]^2."""
+        t = theta * math.pi
+        ph = phi * math.pi * 2.0 - math.pi
+        return (centre[0] + radius * math.cos(ph) * math.sin(t), centre[1] - radius * math.cos(t),
+                centre[2] - radius * math.sin(ph) * math.sin(t))
+
+    @staticmethod
     def plane_map_inverse(radius, centre) -> PlaneMapInverse:
         return PlaneMapInverse(float(radius), tuple(float(x) for x in centre))
 
@@ -260,7 +317,7 @@ class _TextureTable:
         else:
             raise NotImplementedError(
                 "ParameterisedTexture.Arbitrary is a host closure and cannot be evaluated on the device "
-                "(RT_ERR_UNSUPPORTED); bake it to an Image first")
+                "(RT_ERR_UNSUPPORTED); sample it into an Image first with ParameterisedTexture.bake")
         self.entries.append(e)
         return len(self.entries) - 1
 

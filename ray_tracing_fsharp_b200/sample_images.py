@@ -1,4 +1,5 @@
-"""Scene specifications for the five BASELINE.json configs, built with the mirrored
+"""Scene specifications for the five BASELINE.json configs and for the reference's own ray-traced
+sample scenes (REFERENCE_SAMPLES; `random-spheres` and `earth` are C2 and C3), built with the mirrored
 F# surface in domain.py.  They follow RayTracing.App/SampleImages.fs where a sample exists
 (randomSpheres :812-960, earth :962-1010, glassSphere :506-597, movedCamera :710-810) but draw their
 random parameters from a fixed-seed numpy generator instead of `System.Random ()`, so the oracle
@@ -211,6 +212,128 @@ def many_spheres(n=100_000, max_w=1920, max_h=1080, spp=4096, depth=50, seed=5) 
     return SceneSpec(f"C5 synthetic {n} random spheres", objs, spp, 4.0, 16.0 / 9.0, (60.0, 20.0, -60.0),
                      (0.0, 0.0, 0.0), (0.0, 1.0, 0.0), max_w, max_h, depth)
 
+
+# ---- the reference's own sample scenes (RayTracing.App/SampleImages.fs), as parity cases ---------------------
+# Object lists, cameras and half-extents as the sample functions give them; bounce depth 150 (Camera.makeBasic,
+# Camera.fs:43).  `scale` shrinks the half-extents (the samples render up to 4267x2401).  The materials' FloatProducer
+# arguments have no counterpart (the device RNG is keyed per pixel).
+def _sample(name, objs, spp, focal, origin, look_at, pixels, scale):
+    aspect = 16.0 / 9.0
+    max_w, max_h = int(aspect * float(pixels)), pixels  # `aspectRatio * (float pixels) |> int`, e.g. SampleImages.fs:96
+    return SceneSpec(name, objs, spp, focal, aspect, origin, look_at, (0.0, 1.0, 0.0), max(1, int(max_w * scale)),
+                     max(1, int(max_h * scale)), 150)
+
+
+def _sph(style, centre, radius, unbounded=False):
+    s = Sphere.make(style, centre, radius)
+    return Hittable.UnboundedSphere(s) if unbounded else Hittable.Sphere(s)
+
+
+def _col(r, g, b):
+    return Texture.Colour(Pixel(r, g, b))
+
+
+def shiny_floor(scale=1.0) -> SceneSpec:
+    """`shiny-floor`, shinyPlane (SampleImages.fs:57-96): an emitting sphere over a mirror InfinitePlane."""
+    objs = [_sph(SphereStyle.LightSource(_col(0, 255, 255)), (1.5, 0.5, 8.0), 0.5),
+            Hittable.InfinitePlane(InfinitePlane.make(InfinitePlaneStyle.PureReflection(0.5, Colour.White), (0.0, -1.0, 0.0), (0.0, 1.0, 0.0)))]
+    return _sample("shiny-floor", objs, 50, 2.0, (0.0, 0.0, 0.0), (0.0, 0.0, 1.0), 400, scale)
+
+
+def fuzzy_floor(scale=1.0) -> SceneSpec:
+    """`fuzzy-floor`, fuzzyPlane (SampleImages.fs:98-136): the same over a fuzzed InfinitePlane (fuzz 0.75)."""
+    objs = [_sph(SphereStyle.LightSource(_col(0, 255, 255)), (1.5, 0.5, 8.0), 0.5),
+            Hittable.InfinitePlane(InfinitePlane.make(InfinitePlaneStyle.FuzzedReflection(1.0, Colour.White, 0.75), (0.0, -1.0, 0.0), (0.0, 1.0, 0.0)))]
+    return _sample("fuzzy-floor", objs, 50, 2.0, (0.0, 0.0, 0.0), (0.0, 0.0, 1.0), 400, scale)
+
+
+def spheres(scale=1.0) -> SceneSpec:
+    """`spheres` (SampleImages.fs:138-264): four spheres between two mirror planes, a fuzzed floor and a dim emitting
+    plane behind the camera."""
+    r2 = 1.0 / np.sqrt(2.0)
+    objs = [
+        _sph(SphereStyle.LambertReflection(0.95, _col(255, 255, 0)), (0.0, 0.0, 9.0), 1.0),
+        _sph(SphereStyle.PureReflection(1.0, _col(0, 255, 255)), (1.5, 0.5, 8.0), 0.5),
+        _sph(SphereStyle.LightSource(_col(200, 220, 255)), (-1.5, 1.0, 8.0), 0.5),
+        _sph(SphereStyle.FuzzedReflection(1.0, _col(255, 100, 0), 0.2), (-0.4, 1.5, 10.0), 0.25),
+        Hittable.InfinitePlane(InfinitePlane.make(InfinitePlaneStyle.PureReflection(0.8, Colour.White), (0.0, 0.0, 12.0), (r2, 0.0, -r2))),
+        Hittable.InfinitePlane(InfinitePlane.make(InfinitePlaneStyle.FuzzedReflection(0.85, Pixel(255, 100, 100), 0.8), (0.0, -1.0, 0.0), (0.0, 1.0, 0.0))),
+        Hittable.InfinitePlane(InfinitePlane.make(InfinitePlaneStyle.PureReflection(0.95, Colour.White), (0.0, 0.0, 12.0), (-r2, 0.0, -r2))),
+        Hittable.InfinitePlane(InfinitePlane.make(InfinitePlaneStyle.LightSource(_col(15, 15, 15)), (0.0, 1.0, -1.0), (0.0, 0.0, 1.0))),
+    ]
+    return _sample("spheres", objs, 50, 7.0, (0.0, 0.0, 0.0), (0.0, 0.0, 1.0), 200, scale)
+
+
+def inside_sphere(scale=1.0) -> SceneSpec:
+    """`inside-sphere` (SampleImages.fs:266-411): the camera sits inside a bounded r = 100 fuzzed sphere, on top of a
+    bounded r = 75 one; light comes from a bounded r = 9 sphere and a plane behind the camera."""
+    objs = [
+        _sph(SphereStyle.LambertReflection(0.95, _col(255, 255, 0)), (0.0, 0.0, 9.0), 1.0),
+        _sph(SphereStyle.PureReflection(1.0, _col(0, 255, 255)), (1.5, 0.5, 8.0), 0.5),
+        _sph(SphereStyle.PureReflection(1.0, _col(255, 20, 20)), (-1.8, 0.8, 8.0), 0.5),
+        _sph(SphereStyle.LightSource(Texture.Colour(Colour.White)), (-10.0, 8.0, 0.0), 9.0),
+        _sph(SphereStyle.FuzzedReflection(1.0, _col(255, 100, 0), 0.2), (1.4, 1.5, 10.0), 0.25),
+        _sph(SphereStyle.PureReflection(0.9, _col(255, 255, 255)), (0.0, 10.0, 20.0), 8.0),
+        _sph(SphereStyle.FuzzedReflection(0.6, _col(200, 50, 255), 0.4), (0.0, -76.0, 9.0), 75.0),
+        _sph(SphereStyle.FuzzedReflection(0.4, _col(200, 200, 200), 0.0), (0.0, 0.0, 20.0), 100.0),
+        Hittable.InfinitePlane(InfinitePlane.make(InfinitePlaneStyle.LightSource(_col(80, 80, 150)), (0.0, 0.0, -5.0), (0.0, 0.0, 1.0))),
+    ]
+    return _sample("inside-sphere", objs, 50, 7.0, (0.0, 0.0, 0.0), (0.0, 0.0, 1.0), 1200, scale)
+
+
+def _three_on_a_floor(left, right_colour, light, floor_unbounded, light_unbounded):
+    return [
+        _sph(SphereStyle.LambertReflection(0.5, _col(204, 204, 0)), (0.0, -100.5, 1.0), 100.0, floor_unbounded),
+        _sph(SphereStyle.PureReflection(1.0, right_colour), (1.0, 0.0, 1.0), 0.5),
+        _sph(SphereStyle.LambertReflection(1.0, _col(25, 50, 120)), (0.0, 0.0, 1.0), 0.5),
+        _sph(left, (-1.0, 0.0, 1.0), 0.5),
+        _sph(SphereStyle.LightSource(_col(*light)), (0.0, 0.0, 0.0), 200.0, light_unbounded),
+    ]
+
+
+def total_refraction(scale=1.0) -> SceneSpec:
+    """`total-refraction` (SampleImages.fs:413-504): Dielectric 1.5 with refraction probability 1 on a BOUNDED
+    r = 100 floor inside a BOUNDED r = 200 light."""
+    objs = _three_on_a_floor(SphereStyle.Dielectric(1.0, Texture.Colour(Colour.White), 1.5, 1.0), _col(204, 153, 51), (80, 80, 150), False, False)
+    return _sample("total-refraction", objs, 50, 1.0, (0.0, 0.0, 0.0), (0.0, 0.0, 1.0), 300, scale)
+
+
+def glass_sphere(scale=1.0) -> SceneSpec:
+    """`glass` (SampleImages.fs:506-597): Glass 1.5 (albedo 0.9), unbounded floor and light."""
+    objs = _three_on_a_floor(SphereStyle.Glass(0.9, Texture.Colour(Colour.White), 1.5), _col(100, 150, 200), (200, 200, 200), True, True)
+    return _sample("glass", objs, 50, 1.0, (0.0, 0.0, 0.0), (0.0, 0.0, 1.0), 200, scale)
+
+
+def textured_sphere(scale=1.0, bake=(512, 256)) -> SceneSpec:
+    """`textured-sphere` (SampleImages.fs:599-708): as `glass`, the mirror sphere carrying a checker (grid 50) of two
+    closures of (u, v).  The closures are sampled into Images (ParameterisedTexture.bake); the checker stays a checker."""
+    interpret = Sphere.plane_map_inverse(0.5, (1.0, 0.0, 1.0))
+    even = ParameterisedTexture.Arbitrary(lambda x, y: Texture.Colour(Pixel(int(x * 255.0) & 255, 0, int(y * 255.0) & 255)))
+    odd = ParameterisedTexture.Arbitrary(lambda x, y: Texture.Colour(Pixel(100, int(x * 255.0) & 255, int(y * 255.0) & 255)))
+    texture = ParameterisedTexture.Checkered(ParameterisedTexture.bake(even, interpret, *bake), ParameterisedTexture.bake(odd, interpret, *bake), 50.0)
+    objs = _three_on_a_floor(SphereStyle.Glass(0.9, Texture.Colour(Colour.White), 1.5), ParameterisedTexture.to_texture(interpret, texture),
+                             (200, 200, 200), True, True)
+    return _sample("textured-sphere", objs, 50, 1.0, (0.0, 0.0, 0.0), (0.0, 0.0, 1.0), 200, scale)
+
+
+def moved_camera(scale=1.0) -> SceneSpec:
+    """`moved-camera` (SampleImages.fs:710-810): camera at (-2, 2, -1) looking at the glass sphere; the inner shell is a
+    BOUNDED sphere of radius -0.45, which the reference can never hit (F16)."""
+    objs = _three_on_a_floor(SphereStyle.Glass(1.0, Texture.Colour(Colour.White), 1.5), _col(204, 153, 51), (130, 130, 200), False, False)
+    objs.insert(4, _sph(SphereStyle.Glass(1.0, Texture.Colour(Colour.White), 1.0 / 1.5), (-1.0, 0.0, 1.0), -0.45))
+    return _sample("moved-camera", objs, 50, 10.0, (-2.0, 2.0, -1.0), (-1.0, 0.0, 1.0), 300, scale)
+
+
+REFERENCE_SAMPLES = {
+    "shiny-floor": shiny_floor,
+    "fuzzy-floor": fuzzy_floor,
+    "spheres": spheres,
+    "inside-sphere": inside_sphere,
+    "total-refraction": total_refraction,
+    "glass": glass_sphere,
+    "textured-sphere": textured_sphere,
+    "moved-camera": moved_camera,
+}
 
 CONFIGS = {
     "C1": few_spheres,

@@ -363,6 +363,29 @@ def test_plane_map_known_answers_via_checker():
     assert 0.2 < (got[:, 0] == 255).mean() < 0.8
 
 
+def test_baked_closure_texture_on_the_device():
+    """a ParameterisedTexture.Arbitrary closure sampled into an Image (ParameterisedTexture.bake) is
+    looked up on the device exactly as the oracle looks up that Image, and agrees with the closure itself to within
+    the texel grid."""
+    from ray_tracing_fsharp_b200.domain import Hittable, ParameterisedTexture, Pixel, Sphere, SphereStyle, Texture, marshal
+    interpret = Sphere.plane_map_inverse(1.5, (0.5, -1.0, 2.0))
+    closure = ParameterisedTexture.Arbitrary(lambda u, v: Texture.Colour(Pixel(int(255 * u), int(255 * v), 99)))
+    baked = ParameterisedTexture.bake(closure, interpret, 256, 128)
+    objs = [Hittable.Sphere(Sphere.make(SphereStyle.LambertReflection(1.0, ParameterisedTexture.to_texture(interpret, baked)), (0.5, -1.0, 2.0), 1.5))]
+    hs, ts, keep = marshal(objs)
+    dsc = native.SceneHandle(hs, ts, 0, keepalive=keep)
+    osc = oracle.Scene(hs, ts)
+    rng = np.random.default_rng(13)
+    p = f32(1.5 * random_unit_vectors(rng, 50_000) + np.array([0.5, -1.0, 2.0]))
+    prim = np.zeros(len(p), np.int32)
+    want, got = osc.texture(prim, p), dsc.texture(prim, p)
+    assert ((want == got).all(1)).mean() > 0.995
+    uv = np.array([oracle.plane_map_inverse(1.5, (0.5, -1.0, 2.0), q) for q in p[:2000]])
+    direct = np.stack([np.floor(255 * uv[:, 0]), np.floor(255 * uv[:, 1]), np.full(len(uv), 99)], 1)
+    err = np.abs(got[:2000].astype(int) - direct.astype(int))
+    assert err[:, 0].max() <= 3 and err[:, 1].max() <= 4 and err[:, 2].max() == 0, err.max(0)
+
+
 # ---- one path ------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("config", ["C1", "C2", "C3", "C4"])
 def test_trace_samples_match_oracle_sample_for_sample(config):

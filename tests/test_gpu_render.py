@@ -45,6 +45,32 @@ def test_frame_matches_oracle_with_shared_rng(config, max_w, max_h, spp):
     assert np.abs(rgb.astype(int) - ref.astype(int)).mean() < 0.3
 
 
+SAMPLE_SCALES = {"shiny-floor": 0.1, "fuzzy-floor": 0.1, "spheres": 0.25, "inside-sphere": 0.04, "total-refraction": 0.15, "glass": 0.25,
+                 "textured-sphere": 0.25, "moved-camera": 0.15}
+
+
+@pytest.mark.parametrize("name", sorted(sample_images.REFERENCE_SAMPLES))
+def test_reference_sample_scene_matches_oracle_with_shared_rng(name):
+    """The reference's own sample scenes (RayTracing.App/SampleImages.fs; `random-spheres` and `earth` are C2 and C3 above),
+    at reduced half-extents, 50 spp, depth 150 as Camera.makeBasic sets it: bounded spheres of radius 75-200 in the tree,
+    a camera inside a bounded sphere (F10), Dielectric with refraction probability 1, a bounded negative-radius shell
+    (F16), every InfinitePlane style, a checker of two baked closures."""
+    spec = sample_images.REFERENCE_SAMPLES[name](SAMPLE_SCALES[name])
+    osc, dsc, cam = scene_pair(spec)
+    mw, mh = spec.max_width_coord, spec.max_height_coord
+    ref, ref_stats, counters, _ = osc.render(cam, mw, mh, seed=11, rng_mode=1, adaptive=True)
+    rgb, sums, stats = dsc.render(cam, mw, mh, seed=11, adaptive=True, want_sums=True)
+    same_px = (rgb == ref).all(2)
+    same_sums = (sums == ref_stats).all(2)
+    print(f"{name}: {rgb.shape[1]}x{rgb.shape[0]}, {int(stats.paths)} paths, {int(stats.rays)} rays; identical pixels {same_px.mean():.4f}, "
+          f"identical sums {same_sums.mean():.4f}, mean |diff| {np.abs(rgb.astype(int) - ref.astype(int)).mean():.4f}")
+    assert same_px.mean() > 0.995, same_px.mean()  # measured 0.9997-1.0000
+    assert same_sums.mean() > 0.99, same_sums.mean()  # measured 0.9984-1.0000
+    assert abs(int(stats.rays) - counters["rays"]) <= 0.01 * counters["rays"]
+    assert np.abs(rgb.astype(int) - ref.astype(int)).mean() < 0.1
+    assert rgb.max() > 0  # something is lit
+
+
 def test_adaptive_rule_and_counts():
     """F5: count is 2*firstTrial+1 where the two truncated means agree, else spp; spp < 11 gives 2*(spp/2)+1 samples."""
     spec = _small("C1", 80, 45, 16)

@@ -183,6 +183,60 @@ def test_closures_cannot_cross_the_abi():
         marshal([s])
 
 
+def test_bake_samples_a_closure_onto_the_texel_grid_of_the_image_lookup():
+    """a ParameterisedTexture.Arbitrary closure becomes an Image whose texel (x, y) holds the
+    closure's value at the centre of the (u, v) cell that Texture.fs:63-67 maps to (x, y)."""
+    interpret = Sphere.plane_map_inverse(2.0, (1.0, 2.0, 3.0))
+    closure = ParameterisedTexture.Arbitrary(lambda u, v: Texture.Colour(Pixel(int(255 * u), int(255 * v), 7)))
+    with pytest.raises(NotImplementedError):
+        marshal([Hittable.Sphere(Sphere.make(SphereStyle.LambertReflection(1.0, ParameterisedTexture.to_texture(interpret, closure)), (1, 2, 3), 2.0))])
+    w, h = 16, 8
+    baked = ParameterisedTexture.bake(closure, interpret, w, h)
+    assert baked.img.shape == (h, w, 3)
+    rng = np.random.default_rng(3)
+    for u, v in rng.random((200, 2)):
+        x, y = int((1.0 - u) * (w - 1)), int(v * (h - 1))  # the lookup of Texture.fs:63-67
+        got = ParameterisedTexture.colour_at(interpret, baked, u, v).as_tuple()
+        assert got == tuple(int(c) for c in baked.img[y, x])
+        want = closure.f(u, v).pixel.as_tuple()
+        assert abs(got[0] - want[0]) <= 255 / (w - 1) + 1 and abs(got[1] - want[1]) <= 255 / (h - 1) + 1 and got[2] == 7
+    # a closure that wants the point itself (Texture.Arbitrary): planeMap supplies it, and planeMapInverse inverts planeMap
+    by_point = ParameterisedTexture.Arbitrary(lambda u, v: Texture.Arbitrary(lambda p: Pixel(*[int(min(255, abs(c) * 40)) for c in p])))
+    p = Sphere.plane_map(2.0, (1.0, 2.0, 3.0), 0.3, 0.6)
+    assert np.allclose(oracle.plane_map(2.0, (1.0, 2.0, 3.0), 0.3, 0.6), p)
+    assert np.allclose(oracle.plane_map_inverse(2.0, (1.0, 2.0, 3.0), p), (0.3, 0.6))
+    assert ParameterisedTexture.colour_at(interpret, by_point, 0.3, 0.6).as_tuple() == tuple(int(min(255, abs(c) * 40)) for c in p)
+    # a baked checker is the checker (away from its edges), and the result crosses the ABI
+    chk = ParameterisedTexture.Checkered(ParameterisedTexture.Colour(Colour.Red), ParameterisedTexture.Colour(Colour.Blue), 10.0)
+    assert ParameterisedTexture.colour_at(interpret, chk, 0.05, 0.05) == Colour.Blue  # sin(.5) sin(.5) > 0: odd
+    hs, ts, _ = marshal([Hittable.Sphere(Sphere.make(SphereStyle.LambertReflection(1.0, ParameterisedTexture.to_texture(interpret, baked)), (1, 2, 3), 2.0))])
+    assert ts[hs[0].texture].kind == abi.RT_TEX_IMAGE and (ts[hs[0].texture].width, ts[hs[0].texture].height) == (w, h)
+
+
+@pytest.mark.parametrize("name", sorted(sample_images.REFERENCE_SAMPLES))
+def test_reference_sample_scenes_marshal_and_render_on_the_oracle(name):
+    """The reference's own sample scenes as scene specs: they cross the ABI's data layout and the oracle renders them
+    (a lit, deterministic frame); the GPU parity tests compare against exactly these renders."""
+    spec = sample_images.REFERENCE_SAMPLES[name](0.02)
+    assert spec.bounce_depth == 150 and spec.spp == 50  # Camera.makeBasic 50 ..., Camera.fs:43
+    hs, ts, _keep = marshal(spec.objects)
+    assert len(hs) == len(spec.objects)
+    cam = oracle.camera_make_basic(spec.spp, spec.focal_length, spec.aspect_ratio, spec.origin, spec.view_direction, spec.view_up)
+    cam.bounce_depth = spec.bounce_depth
+    a, sa, ca, _ = oracle.Scene(hs, ts).render(cam, spec.max_width_coord, spec.max_height_coord, seed=3, rng_mode=1, adaptive=True)
+    b, sb, _, _ = oracle.Scene(hs, ts).render(cam, spec.max_width_coord, spec.max_height_coord, seed=3, rng_mode=1, adaptive=True)
+    assert a.shape == (spec.rows, spec.cols, 3) and np.array_equal(sa, sb) and a.max() > 0 and ca["rays"] >= ca["paths"] > 0
+    if name == "moved-camera":  # F16: the bounded inner shell (radius -0.45) has an inverted box and is never the closest hit
+        n = 4000
+        rng = np.random.default_rng(5)
+        o = np.tile(np.array(spec.origin, float), (n, 1))
+        target = np.array([-1.0, 0.0, 1.0]) + 0.4 * rng.normal(size=(n, 3)) / 3
+        d = target - o
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        prim, _, _, _ = oracle.Scene(hs, ts).hit_object(o, d)
+        assert (prim == 3).sum() > 1000 and not (prim == 4).any()
+
+
 def test_marshal_preserves_texture_structure():
     interpret = Sphere.plane_map_inverse(2.0, (1.0, 2.0, 3.0))
     img = np.arange(4 * 6 * 3, dtype=np.uint8).reshape(4, 6, 3)
