@@ -15,8 +15,16 @@ from helpers import scene_pair  # noqa: E402
 from ray_tracing_fsharp_b200 import sample_images  # noqa: E402
 from ray_tracing_fsharp_b200.scene import ImageOutput  # noqa: E402
 
-for name, mw, mh in [("C1", 200, 112), ("C2", 150, 100), ("C3", 120, 67), ("C4", 120, 67)]:
-    spec = sample_images.CONFIGS[name]()
+# the BASELINE configs at reduced half-extents, then the reference's other sample scenes (SampleImages.fs) likewise
+CASES = [(name, sample_images.CONFIGS[name](), mw, mh) for name, mw, mh in [("C1", 200, 112), ("C2", 150, 100), ("C3", 120, 67), ("C4", 120, 67)]]
+for name, scale in [("shiny-floor", 0.1), ("fuzzy-floor", 0.1), ("spheres", 0.25), ("inside-sphere", 0.04), ("total-refraction", 0.15), ("glass", 0.25),
+                    ("textured-sphere", 0.25), ("moved-camera", 0.15)]:
+    sp = sample_images.REFERENCE_SAMPLES[name](scale)
+    CASES.append((name, sp, sp.max_width_coord, sp.max_height_coord))
+if len(sys.argv) > 1:
+    CASES = [c for c in CASES if c[0] in sys.argv[1:]]
+
+for name, spec, mw, mh in CASES:
     spec.spp = 4096
     osc, dsc, cam = scene_pair(spec)
     t0 = time.perf_counter()

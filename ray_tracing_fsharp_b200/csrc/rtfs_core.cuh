@@ -45,6 +45,38 @@ enum Cmp { CMP_GREATER = 0, CMP_EQUAL = 1, CMP_LESS = 2 };
 RTFS_HD Cmp fcmp(float a, float b) { return (fabsf(a - b) < kTolF) ? CMP_EQUAL : (a < b ? CMP_LESS : CMP_GREATER); }
 RTFS_HD Cmp fcmp(double a, double b) { return (fabs(a - b) < kTolD) ? CMP_EQUAL : (a < b ? CMP_LESS : CMP_GREATER); }
 
+// ---- one-instruction reciprocal / square root -----------------------------------------------------
+// For arguments known to be normal numbers (or zero, for sqrt): a single MUFU (<= 2 ulp) instead of the IEEE
+// sequences with their denormal rescaling and slow paths (4 to 12 instructions each, several per bounce).  The
+// contract on this path is 1e-5 relative; decisions against the reference's 1e-8 tolerances move by an ulp or two.
+RTFS_HD float rcp_fast(float x) { // 1 / x for |x| in the normal range: one MUFU.RCP (1 ulp), no denormal rescaling
+#ifdef __CUDA_ARCH__
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / x;
+#endif
+}
+RTFS_HD float rsqrt_fast(float x) { // 1 / sqrt(x), x a normal number: one MUFU.RSQ
+#ifdef __CUDA_ARCH__
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / sqrtf(x);
+#endif
+}
+RTFS_HD float sqrt_fast(float x) {
+#ifdef __CUDA_ARCH__
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return sqrtf(x);
+#endif
+}
+
 // ---- vectors (Point.fs:17-100) ------------------------------------------------------------------
 RTFS_HD float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
 RTFS_HD float3 operator+(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
@@ -57,8 +89,7 @@ RTFS_HD float3 fma3(float s, float3 a, float3 b) { return f3(fmaf(s, a.x, b.x), 
 RTFS_HD bool unitise(float3 v, float3 &out) {
     float d = dot(v, v);
     if (fabsf(d) < kTolF) return false;
-    out = rsqrtf(d) * v;
-    // one Newton step is not needed: rsqrtf is 2 ulp; renormalisation error stays ~1e-7
+    out = rsqrt_fast(d) * v; // d >= 1e-8: a normal number; 2 ulp, renormalisation error stays ~1e-7
     return true;
 }
 
@@ -152,27 +183,6 @@ RTFS_HD bool camera_ray(const DevCamera &c, int row, int col, float r1, float r2
                   fmaf(walk, c.yz, fmaf(landing, c.xz, c.cz)));
     o = f3(c.ox, c.oy, c.oz);
     return unitise(v, d);
-}
-
-// sqrt for an argument known to be a normal number: one MUFU.SQRT (2 ulp) instead of the ten-instruction IEEE
-// sequence; the hit distance only has to hold 1e-5 relative
-RTFS_HD float rcp_fast(float x) { // 1 / x for |x| in the normal range: one MUFU.RCP (1 ulp), no denormal rescaling
-#ifdef __CUDA_ARCH__
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-#else
-    return 1.0f / x;
-#endif
-}
-RTFS_HD float sqrt_fast(float x) {
-#ifdef __CUDA_ARCH__
-    float r;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-#else
-    return sqrtf(x);
-#endif
 }
 
 // ---- BoundingBox.hits with inverseDirections (BoundingBox.fs:25-94) -----------------------------------
@@ -275,7 +285,7 @@ RTFS_HD bool sphere_hit(float3 o, float3 d, float4 s, bool self, float &t_out) {
 RTFS_HD bool sphere_hit_big(D3 o, D3 d, double a, const DUnbounded &s, bool self, float &t_out) {
     D3 oc = o - D3{s.p[0], s.p[1], s.p[2]};
     double b = dot(d, oc);
-    float inv_a = 1.0f / float(a);
+    float inv_a = rcp_fast(float(a)); // a = d.d ~ 1
     if (self) { // c = 0: roots 0 and -2b / a; the reference keeps the one that is `positive`
         float t = -2.0f * float(b) * inv_a;
         t_out = t;
@@ -289,15 +299,15 @@ RTFS_HD bool sphere_hit_big(D3 o, D3 d, double a, const DUnbounded &s, bool self
     } else if (disc < 0.0f) {
         return false;
     } else {
-        float im = sqrtf(disc);
+        float im = sqrt_fast(disc); // disc >= 1e-8 here
         float q1 = im - bf, q2 = -(bf + im); // i1 = q1 / a (the larger root), i2 = q2 / a; q1 * q2 = a * c
         float i1, i2;
-        if (bf < 0.0f) {
+        if (bf < 0.0f) { // |q1| >= im >= 1e-4
             i1 = q1 * inv_a;
-            i2 = cf / q1;
-        } else {
+            i2 = cf * rcp_fast(q1);
+        } else { // |q2| >= im >= 1e-4
             i2 = q2 * inv_a;
-            i1 = (q2 != 0.0f) ? cf / q2 : 0.0f;
+            i1 = cf * rcp_fast(q2);
         }
         bool p1 = i1 > kTolF, p2 = i2 > kTolF;
         if (p1 && p2)
@@ -318,7 +328,7 @@ RTFS_HD bool plane_hit_big(D3 o, D3 d, const DUnbounded &p, bool self, float &t_
     D3 n{double(p.n[0]), double(p.n[1]), double(p.n[2])};
     float den = float(dot(n, d));
     if (fabsf(den) < kTolF) return false;
-    float t = float(dot(n, D3{p.p[0], p.p[1], p.p[2]} - o)) / den;
+    float t = float(dot(n, D3{p.p[0], p.p[1], p.p[2]} - o)) * rcp_fast(den); // |den| >= 1e-8
     t_out = t;
     return t > kTolF;
 }
@@ -612,7 +622,7 @@ RTFS_HD uint32_t texture_colour(const SceneGlobal &g, int tex, float3 p) {
     float3 q = t.inv_radius * f3(p.x - t.cx, p.y - t.cy, p.z - t.cz);
     float theta = acosf(fminf(1.0f, fmaxf(-1.0f, -q.y)));
     float phi = atan2f(-q.z, q.x) + CUDART_PI_F;
-    float u = phi / (2.0f * CUDART_PI_F), v = theta / CUDART_PI_F;
+    float u = phi * (0.5f / CUDART_PI_F), v = theta * (1.0f / CUDART_PI_F); // constants fold; a multiply instead of an IEEE division
     for (int guard = 0; guard < 8 && t.kind == RT_TEX_CHECKERED; ++guard) { // Texture.fs:56-62
         float sine = sinf(t.grid * u) * sinf(t.grid * v);
         t = g.tex[(fcmp(sine, 0.0f) == CMP_LESS) ? t.even : t.odd];
@@ -665,13 +675,13 @@ RTFS_HD float3 reflect_dir(float3 n, float3 d, float nd, float3 tangent) {
 }
 // Sphere.refract (Sphere.fs:108-146); `refl` is what reflectWithoutFuzz gives (total internal reflection)
 RTFS_HD float3 refract_dir(bool inside, float3 n, float3 d, float3 tangent, float3 refl, float incoming_cos, float ior) {
-    float index = inside ? 1.0f / ior : ior;
+    float inv_index = inside ? ior : rcp_fast(ior); // 1 / index, index = inside ? 1 / ior : ior (Sphere.fs:118-119)
     float3 tu;
     if (!unitise(tangent, tu)) return d; // parallel to the normal: straight through
-    float incoming_sin = sqrtf(fmaxf(0.0f, 1.0f - incoming_cos * incoming_cos));
-    float outgoing_sin = incoming_sin / index;
+    float incoming_sin = sqrt_fast(fmaxf(0.0f, 1.0f - incoming_cos * incoming_cos));
+    float outgoing_sin = incoming_sin * inv_index;
     if (fcmp(outgoing_sin, 1.0f) == CMP_GREATER) return refl;
-    float outgoing_cos = sqrtf(fmaxf(0.0f, 1.0f - outgoing_sin * outgoing_sin));
+    float outgoing_cos = sqrt_fast(fmaxf(0.0f, 1.0f - outgoing_sin * outgoing_sin));
     float3 v = fma3(outgoing_sin, tu, (-outgoing_cos) * n);
     float3 out;
     if (!unitise(v, out)) return d;
@@ -765,8 +775,8 @@ RTFS_HD ScatterResult scatter(const SceneAccess<SMEM> &sc, int prim, int last, f
         if (!(u.x > m.p1)) out = refract_dir(inside, n, d, tangent, refl, nd, m.p0);
     } else if (style == RT_STYLE_GLASS) { // Sphere.fs:269-300
         float incoming_cos = -nd;
-        float refr = inside ? 1.0f / m.p0 : m.p0;
-        float param = (1.0f - refr) / (1.0f + refr);
+        float refr = inside ? rcp_fast(m.p0) : m.p0;
+        float param = (1.0f - refr) * rcp_fast(1.0f + refr);
         param = param * param;
         float x = 1.0f - incoming_cos;
         float x2 = x * x;
