@@ -153,6 +153,28 @@ module GpuTexture =
 
         t
 
+    /// Samples a `ParameterisedTexture` (typically an `Arbitrary` closure, which cannot run on the GPU) into an
+    /// `Image` of `width` x `height` texels.  Texel (x, y) of an Image answers the lookups with
+    /// `int ((1 - u) (W - 1)) = x` and `int (v (H - 1)) = y` (Texture.fs:63-67); it receives the texture's value
+    /// at the centre of that cell.  An approximation by construction, hence explicit (same as
+    /// `ParameterisedTexture.bake` in the Python mirror, domain.py).
+    let bake (radius : float) (centre : Point) (width : int) (height : int) (texture : ParameterisedTexture) : ParameterisedTexture =
+        let interpret = Sphere.planeMapInverse radius centre
+
+        Array.init
+            height
+            (fun y ->
+                let v = min 1.0 ((float y + 0.5) / float (height - 1))
+
+                Array.init
+                    width
+                    (fun x ->
+                        let u = max 0.0 (1.0 - (float x + 0.5) / float (width - 1))
+                        ParameterisedTexture.colourAt interpret texture (Sphere.planeMap radius centre u v)
+                    )
+            )
+        |> ParameterisedTexture.Image
+
     let internal tryStructure (t : Texture) : (float * Point * ParameterisedTexture) voption =
         match t with
         | Texture.Colour _ -> ValueNone
@@ -161,7 +183,7 @@ module GpuTexture =
             | true, v -> ValueSome v
             | false, _ ->
                 failwith
-                    "GPU backend: Texture.Arbitrary is a host closure; build it with GpuTexture.ofParameterised (or bake it to an Image)"
+                    "GPU backend: Texture.Arbitrary is a host closure; build it with GpuTexture.ofParameterised (closures inside it: GpuTexture.bake)"
 
 type GpuScene =
     private
