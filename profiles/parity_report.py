@@ -16,7 +16,8 @@ from ray_tracing_fsharp_b200 import sample_images  # noqa: E402
 from ray_tracing_fsharp_b200.scene import ImageOutput  # noqa: E402
 
 # the BASELINE configs at reduced half-extents, then the reference's other sample scenes (SampleImages.fs) likewise
-CASES = [(name, sample_images.CONFIGS[name](), mw, mh) for name, mw, mh in [("C1", 200, 112), ("C2", 150, 100), ("C3", 120, 67), ("C4", 120, 67)]]
+CASES = [(name, sample_images.CONFIGS[name](), mw, mh) for name, mw, mh in [("C1", 200, 112), ("C2", 150, 100), ("C3", 120, 67), ("C4", 120, 67),
+                                                                            ("C5", 60, 34)]]
 for name, scale in [("shiny-floor", 0.1), ("fuzzy-floor", 0.1), ("spheres", 0.25), ("inside-sphere", 0.04), ("total-refraction", 0.15), ("glass", 0.25),
                     ("textured-sphere", 0.25), ("moved-camera", 0.15)]:
     sp = sample_images.REFERENCE_SAMPLES[name](scale)

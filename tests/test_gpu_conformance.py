@@ -387,20 +387,29 @@ def test_baked_closure_texture_on_the_device():
 
 
 # ---- one path ------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("config", ["C1", "C2", "C3", "C4"])
+@pytest.mark.parametrize("config", ["C1", "C2", "C3", "C4", "C5"])
 def test_trace_samples_match_oracle_sample_for_sample(config):
     spec = sample_images.CONFIGS[config]()
     osc, dsc, cam = scene_pair(spec)
     rng = np.random.default_rng(13)
-    n = 30_000
+    n = 30_000 if config != "C5" else 8_000  # the oracle walks the 100 k-sphere reference tree exhaustively
     row = rng.integers(0, spec.rows, n).astype(np.int32)
     col = rng.integers(0, spec.cols, n).astype(np.int32)
     smp = rng.integers(0, spec.spp, n).astype(np.int32)
     wc, wr = osc.trace_samples(cam, spec.max_width_coord, spec.max_height_coord, 99, row, col, smp)
     gc, gr = dsc.trace_samples(cam, spec.max_width_coord, spec.max_height_coord, 99, row, col, smp)
     same = (wc == gc).all(1)
-    assert same.mean() > 0.998, same.mean()         # FP32 flips a decision on a few paths; they then diverge
-    assert (wr == gr).mean() > 0.998
+    if config != "C5":
+        assert same.mean() > 0.998, same.mean()         # FP32 flips a decision on a few paths; they then diverge
+        assert (wr == gr).mean() > 0.998
+    else:
+        # Spheres of radius 0.05-0.3 at |x| ~ 50-90: an FP32 strike point is off by ~4e-6, i.e. 1e-4 of such a radius in the
+        # normal, and every bounce off so small a sphere magnifies a direction error by ~distance / radius ~ 100.  After
+        # two or three bounces the FP32 and FP64 trajectories part (measured: 9 % of paths end with another ray count),
+        # by which time the integer colour is mostly black already (measured: 99.25 % of paths give identical bytes).
+        # Unbiased all the same: the means agree to 0.015 of 255 here and the 4096-spp report covers the scene.
+        assert same.mean() > 0.985, same.mean()
+        assert (wr == gr).mean() > 0.85
     assert np.abs(gc.astype(float).mean(0) - wc.astype(float).mean(0)).max() < 0.5
 
 

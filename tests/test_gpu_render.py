@@ -261,6 +261,40 @@ def test_full_size_properties_c2():
     assert (a[0, 0] == np.array([200, 200, 255], np.uint8)).all() and sa[0, 0, 3] == 11
 
 
+@pytest.mark.parametrize("config,spp", [("C3", None), ("C4", None), ("C5", 12)])
+def test_full_size_properties_other_configs(config, spp):
+    """BASELINE.json's other configs at their full frame sizes (C3, C4 at their full spp; the 100 k-sphere C5, whose tree
+    is read from L2, at 12 spp): determinism, the early-out accounting, the accumulator invariants, and the two-rank
+    sample split summing to the single-rank frame bit for bit."""
+    import torch
+    from ray_tracing_fsharp_b200.distributed import DeviceBackend
+    spec = sample_images.CONFIGS[config]()
+    if spp:
+        spec.spp = spp
+    hs, ts, keep = marshal(spec.objects)
+    dsc = native.SceneHandle(hs, ts, 0, keepalive=keep)
+    cam = oracle_camera(spec)
+    mw, mh = spec.max_width_coord, spec.max_height_coord
+    a, sa, sta = dsc.render(cam, mw, mh, seed=3, want_sums=True)
+    b, sb, stb = dsc.render(cam, mw, mh, seed=3, want_sums=True)
+    assert a.shape == (spec.rows, spec.cols, 3) and (dsc.shared_memory_bytes() == 0) == (config == "C5")
+    assert np.array_equal(sa, sb) and int(sta.rays) == int(stb.rays)
+    assert set(np.unique(sa[..., 3]).tolist()) <= {11, spec.spp}
+    assert int(sta.paths) == int(sa[..., 3].sum()) and int(sta.pixels_early_out) == int((sa[..., 3] == 11).sum())
+    assert (sa[..., :3] <= 255 * sa[..., 3:4]).all() and (sa[..., :3] >= 0).all()
+    assert np.array_equal(a, (sa[..., :3] // sa[..., 3:4]).astype(np.uint8))
+    backends = [DeviceBackend(dsc, cam, mw, mh, seed=3, adaptive=True) for _ in range(2)]
+    bufs = [be.alloc() for be in backends]
+    for r in range(2):
+        backends[r].probe(r, 2, *bufs[r])
+    flags = torch.maximum(bufs[0][1], bufs[1][1])  # all_reduce(MAX)
+    for r in range(2):
+        bufs[r][1].copy_(flags)
+        backends[r].main(r, 2, *bufs[r])
+    total = (bufs[0][0] + bufs[1][0]).cpu().numpy().reshape(sa.shape)  # all_reduce(SUM)
+    assert np.array_equal(total, sa)
+
+
 def test_errors_are_codes_not_crashes():
     lib = native.lib()
     cam = Camera.make_basic(4, 1.0, 1.0, (0.0, 0.0, 0.0), (0.0, 0.0, 1.0), (0.0, 1.0, 0.0))
