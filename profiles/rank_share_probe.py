@@ -14,7 +14,7 @@ from ray_tracing_fsharp_b200.scene import Camera  # noqa: E402
 
 spec = sample_images.CONFIGS[sys.argv[1] if len(sys.argv) > 1 else "C2"]()
 cam = Camera.make_basic(spec.spp, spec.focal_length, spec.aspect_ratio, spec.origin, spec.view_direction, spec.view_up)
-cam.bounce_depth = spec.bounce_depth
+cam.bounce_depth = int(sys.argv[2]) if len(sys.argv) > 2 else spec.bounce_depth  # a lower budget shortens the longest paths (the tail)
 hs, ts, keep = marshal(spec.objects)
 scene = native.SceneHandle(hs, ts, 0, keepalive=keep)
 mw, mh = spec.max_width_coord, spec.max_height_coord
