@@ -34,6 +34,8 @@ class Image:
     Rows: Sequence[Callable[[], np.ndarray]]
     RowCount: int
     ColCount: int
+    # set by Scene.render: forces every row at once (one frame, one progress call per row) without 2·maxH+1 array copies
+    _all_rows: Optional[Callable[[], np.ndarray]] = None
 
     @staticmethod
     def row_count(i: "Image") -> int:
@@ -46,6 +48,8 @@ class Image:
     @staticmethod
     def render(i: "Image") -> np.ndarray:
         """Image.render (Domain.fs:23-24): force every row; returns uint8 [rows, cols, 3]."""
+        if i._all_rows is not None:
+            return i._all_rows()
         return np.stack([row() for row in i.Rows]) if i.RowCount else np.zeros((0, i.ColCount, 3), np.uint8)
 
 
@@ -105,7 +109,13 @@ class Scene:
                 return out
             return force
 
-        return float(rows), Image([row_thunk(r) for r in range(rows)], rows, cols)
+        def all_rows():
+            out = frame()
+            for _ in range(rows):
+                progress_increment(1.0)
+            return out
+
+        return float(rows), Image([row_thunk(r) for r in range(rows)], rows, cols, all_rows)
 
 
 class PixelOutput:

@@ -175,6 +175,10 @@ def test_scene_render_surface_and_ppm_bytes():
     assert total == 45.0 and Image.row_count(image) == 45 and Image.col_count(image) == 81 and ticks == []  # lazy
     pixels = Image.render(image)
     assert len(ticks) == 45 and pixels.shape == (45, 81, 3)
+    # rows can also be forced one at a time, as `Image.Rows` consumers do (ImageOutput.fs:142): one tick per row
+    ticks2 = []
+    _, image2 = Scene.render(ticks2.append, lambda s: None, 40, 22, cam, scene, seed=11)
+    assert np.array_equal(image2.Rows[3](), pixels[3]) and np.array_equal(image2.Rows[44](), pixels[44]) and len(ticks2) == 2
     # PPM bytes: the device result through the library's writer == the oracle's writer on the same pixels
     assert ImageOutput.write_ppm(False, pixels) == oracle.ppm_format(pixels, False)
     assert ImageOutput.write_ppm(True, pixels) == oracle.ppm_format(pixels, True)
