@@ -181,10 +181,11 @@ __global__ void k_trace_samples(SceneGlobal g, DevCamera cam, uint32_t k0, uint3
     uint32_t result = kBlack;
     int rays = 0;
     TraversalCounters cn{0, 0};
+    LocalStack stack;
     if (path_begin(ps, cam, k0, k1, row_idx[i], col_idx[i], uint32_t(sample[i]))) {
         for (;;) {
             ++rays;
-            if (path_step<false, false>(ps, sc, cam.depth, result, cn, 1u << (threadIdx.x & 31))) break; // lanes run independently here
+            if (path_step<false, false>(ps, sc, cam.depth, result, cn, 1u << (threadIdx.x & 31), stack)) break; // lanes run independently here
         }
     }
     colour_out[3 * i] = uint8_t(result >> 16);

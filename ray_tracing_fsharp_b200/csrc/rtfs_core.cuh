@@ -447,6 +447,27 @@ struct TraversalCounters {
     uint32_t box_tests, prim_tests;
 };
 
+// The walk's stack of postponed children: a per-thread array in local memory, or (render kernels, when shared memory
+// has room for tree depth x block size words) a column of shared memory per thread.  Thread t's entry i sits at word
+// i * blockDim + t: lanes are always in distinct banks, whatever their depths, so a push or pop is one conflict-free
+// wavefront, where lanes at different depths of a local-memory stack touch a cache line each.
+struct LocalStack {
+    int a[64];
+    RTFS_HD void put(int i, int v) { a[i] = v; }
+    RTFS_HD int get(int i) const { return a[i]; }
+};
+#ifdef __CUDACC__
+struct SharedStack {
+    uint32_t base, stride; // byte address of this thread's entry 0 in the shared window; bytes between entries
+    __device__ __forceinline__ void put(int i, int v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(base + uint32_t(i) * stride), "r"(v)); }
+    __device__ __forceinline__ int get(int i) const {
+        int v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base + uint32_t(i) * stride));
+        return v;
+    }
+};
+#endif
+
 // Scene.hitObject (Scene.fs:62-91) over the SAH tree: ordered, culled by the best hit so far.  The
 // closest hit does not depend on tree topology or visiting order (only exact ties in t do, F12), so the
 // result equals the reference's exhaustive left-then-right DFS.  Then the unbounded objects in array
@@ -454,8 +475,8 @@ struct TraversalCounters {
 // One visit of the walk over the tree: `node` is an internal node (>= 0: test both children's boxes, descend into
 // the nearer one, push the other) or a leaf (~k: test sphere k, pop).  Returns true when the walk is over.
 // `node`, `last_ref`, `best` and the stack entries are refs (SceneAccess); best >= 0 (kNoRef): nothing hit yet.
-template <bool SMEM, bool COUNT>
-RTFS_HD bool bvh_visit(const SceneAccess<SMEM> &sc, const RaySlabs &rs, float3 o, float3 d, int last_ref, int &node, int &sp, int *stack,
+template <bool SMEM, bool COUNT, class Stack>
+RTFS_HD bool bvh_visit(const SceneAccess<SMEM> &sc, const RaySlabs &rs, float3 o, float3 d, int last_ref, int &node, int &sp, Stack &stack,
                        float &best_t, int &best, TraversalCounters &cn) {
     if (node >= 0) {
         uint4 q0, q1, q2, q3;
@@ -469,7 +490,7 @@ RTFS_HD bool bvh_visit(const SceneAccess<SMEM> &sc, const RaySlabs &rs, float3 o
         int left = int(q3.x), right = int(q3.y);
         if (hl && hr) {
             bool left_first = tl <= tr;
-            stack[sp++] = left_first ? right : left;
+            stack.put(sp++, left_first ? right : left);
             node = left_first ? left : right;
             return false;
         }
@@ -485,7 +506,7 @@ RTFS_HD bool bvh_visit(const SceneAccess<SMEM> &sc, const RaySlabs &rs, float3 o
         }
     }
     if (sp == 0) return true;
-    node = stack[--sp];
+    node = stack.get(--sp);
     return false;
 }
 // A path remembers the primitive its ray leaves as the walk names it: the leaf ref of a bounded sphere (< 0), the
@@ -495,13 +516,13 @@ RTFS_HD int ref_of_prim(const SceneAccess<SMEM> &sc, int prim) {
     return prim < 0 ? kNoRef : (prim < sc.g.n_bounded ? sc.ref_of_sphere(prim) : prim);
 }
 // the bounded part of hitObject: the closest sphere of the tree, if any
-template <bool SMEM, bool COUNT>
-RTFS_HD void bvh_closest(const SceneAccess<SMEM> &sc, float3 o, float3 d, int last_ref, float &best_t, int &best_ref, TraversalCounters &cn) {
+template <bool SMEM, bool COUNT, class Stack>
+RTFS_HD void bvh_closest(const SceneAccess<SMEM> &sc, float3 o, float3 d, int last_ref, float &best_t, int &best_ref, TraversalCounters &cn,
+                         Stack &stack) {
     best_t = kNoHitT;
     best_ref = kNoRef;
     if (sc.g.n_bounded <= 0) return;
     const RaySlabs rs = make_slabs(o, d);
-    int stack[64];
     int sp = 0;
     int node = sc.root();
     while (!bvh_visit<SMEM, COUNT>(sc, rs, o, d, last_ref, node, sp, stack, best_t, best_ref, cn)) {
@@ -541,18 +562,19 @@ RTFS_HD Hit finish_hit(const SceneAccess<SMEM> &sc, float3 o, float3 d, int last
 // full width instead of once per straggler group.
 // (Tried and dropped: parking a leaf and testing it after the walk, converged, instead of during it at ~4 active
 // lanes — the lost culling costs 5 % more slab tests and the C2 frame got 3 % slower.)
-template <bool SMEM, bool COUNT>
-RTFS_HD Hit closest_hit_from(const SceneAccess<SMEM> &sc, float3 o, float3 d, int last_ref, TraversalCounters &cn, unsigned lanes) {
+template <bool SMEM, bool COUNT, class Stack>
+RTFS_HD Hit closest_hit_from(const SceneAccess<SMEM> &sc, float3 o, float3 d, int last_ref, TraversalCounters &cn, unsigned lanes, Stack &stack) {
     float best_t;
     int best_ref;
-    bvh_closest<SMEM, COUNT>(sc, o, d, last_ref, best_t, best_ref, cn);
+    bvh_closest<SMEM, COUNT>(sc, o, d, last_ref, best_t, best_ref, cn, stack);
     converge(lanes);
     return finish_hit<SMEM, COUNT>(sc, o, d, last_ref, best_t, best_ref, cn);
 }
 // the same with the ray's previous primitive given as a device primitive id (conformance entry points, wavefront)
 template <bool SMEM, bool COUNT>
 RTFS_HD Hit closest_hit(const SceneAccess<SMEM> &sc, float3 o, float3 d, int last, TraversalCounters &cn, unsigned lanes) {
-    return closest_hit_from<SMEM, COUNT>(sc, o, d, ref_of_prim(sc, last), cn, lanes);
+    LocalStack stack;
+    return closest_hit_from<SMEM, COUNT>(sc, o, d, ref_of_prim(sc, last), cn, lanes, stack);
 }
 
 // The reference's own traversal (Scene.fs:30-60, F12): exhaustive left-then-right DFS of the
@@ -855,9 +877,10 @@ RTFS_HD bool path_after_hit(PathState &p, const SceneAccess<SMEM> &sc, const Hit
     return false;
 }
 // one whole step: hitObject + Reflection; returns true when the path is finished
-template <bool SMEM, bool COUNT>
-RTFS_HD bool path_step(PathState &p, const SceneAccess<SMEM> &sc, int max_count, uint32_t &result, TraversalCounters &cn, unsigned lanes) {
-    Hit h = closest_hit_from<SMEM, COUNT>(sc, p.o, p.d, p.last, cn, lanes);
+template <bool SMEM, bool COUNT, class Stack>
+RTFS_HD bool path_step(PathState &p, const SceneAccess<SMEM> &sc, int max_count, uint32_t &result, TraversalCounters &cn, unsigned lanes,
+                       Stack &stack) {
+    Hit h = closest_hit_from<SMEM, COUNT>(sc, p.o, p.d, p.last, cn, lanes, stack);
     return path_after_hit<SMEM>(p, sc, h, max_count, result);
 }
 

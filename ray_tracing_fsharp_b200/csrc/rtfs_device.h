@@ -70,6 +70,7 @@ struct DeviceScene {
     void *blob = nullptr; // one allocation holding nodes | spheres | materials | unbounded | reference nodes | textures
     std::vector<PooledTexture> images; // image textures borrowed from the pool
     size_t bytes = 0;
+    int32_t max_depth = 0; // depth of the tree: the walk's stack never holds more entries
     DeviceWorkspace *ws = nullptr;
 };
 
@@ -101,6 +102,7 @@ struct FrameParams {
     unsigned long long *counters;
     // shared-memory staging
     uint32_t s_nodes, s_spheres, s_mats, s_warp; // offsets in uint4 units
+    uint32_t s_stack; // SSTACK kernels: the walk stacks, one column of `stack_levels` words per thread (uint4 units)
 };
 
 
