@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) render_kernel(const FramePar
         const int j_begin = int(fp.chunk_begin[k]), j_len = int(fp.chunk_len[k]);
         int my_pixel = -1;
         n_entries = 32;
-        if (PROBE) {
+        if constexpr (PROBE) {
             int tile = int(unit) * fp.world + fp.rank;
             int ty = tile / fp.tiles_x, tx = tile - ty * fp.tiles_x;
             int r = ty * kTileH + (lane >> 3), c = tx * kTileW + (lane & 7);
