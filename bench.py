@@ -292,7 +292,7 @@ def run_ours(args):
     e2e_rays = 0
     h2d = d2h = 0
     n_e2e = max(1, min(args.steps, 3))
-    for i in range(-1, n_e2e):  # iteration -1 is an untimed warm-up (first-use allocations of a fresh handle)
+    for i in range(-2, n_e2e):  # two untimed warm-up iterations (first-use allocations: handle pool, the two recycled output frames)
         barrier()
         t0 = time.perf_counter()
         if world == 1:
