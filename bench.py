@@ -310,7 +310,7 @@ def run_ours(args):
             be = DeviceBackend(sc2, cam, max_w, max_h, seed=3000 + i, adaptive=adaptive, flags=flags)
             stats_t, _ = render_split_frame(be, rank, world, red_max, red_sum)
             if rank == 0:
-                pixels = be.finalize(stats_t).cpu().numpy()
+                pixels = be.finalize_to_host(stats_t)  # device->host copy of the frame into pinned host memory
                 d2h = pixels.nbytes + 64
             torch.cuda.synchronize(dev)
             r_rays = be.counters().rays
@@ -365,7 +365,9 @@ def run_ours(args):
             "rays_per_step": rays / args.steps, "paths_per_step": paths / args.steps,
             "e2e": {"value": e2e_rays / e2e_secs / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * e2e_secs / n_e2e, "steps": n_e2e,
-                    "what": "Scene.make (BVH build + upload) + Scene.render + Image.render with host buffers"},
+                    "what": ("Scene.make (BVH build + upload) + Scene.render + Image.render with host buffers" if world == 1 else
+                             "per rank: marshal + rt_scene_create (BVH build + upload) + rt_device_probe / all-reduce / rt_device_main / all-reduce; "
+                             "rank 0: rt_device_finalize + device->host copy of the frame into pinned host memory")},
             "gpu_launches": int(launch_t.item()),
             "clocks": clocks,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak if fp32_peak else None,

@@ -73,6 +73,22 @@ class DeviceBackend:
         self.launches += 1
         return self._rgb
 
+    _host_frames = {}  # n_pixels -> two pinned host frames, used alternately
+
+    def finalize_to_host(self, stats, gamma=False):
+        """finalize + device->host copy of the RGB8 frame into a recycled PINNED host buffer (a fresh pageable tensor costs
+        the copy a page fault per 4 KiB: 1.3 ms of a 12 ms 8-GPU frame).  Returns a uint8 numpy view [n_pixels, 3] that
+        stays valid until the call after next."""
+        torch = self.torch
+        ring = DeviceBackend._host_frames.setdefault(self.n_pixels, [[], 0])
+        if len(ring[0]) < 2:
+            ring[0].append(torch.empty((self.n_pixels, 3), dtype=torch.uint8, pin_memory=True))
+        host = ring[0][ring[1] % len(ring[0])]
+        ring[1] += 1
+        host.copy_(self.finalize(stats, gamma), non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return host.numpy()
+
     def counters(self) -> abi.RtStats:
         """Work counters (paths, rays, ...) of this rank since the last probe; synchronises the stream."""
         out = abi.RtStats()

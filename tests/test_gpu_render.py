@@ -216,6 +216,7 @@ def test_sample_split_is_invariant_emulated_on_one_gpu():
         assert np.array_equal(total.cpu().numpy().reshape(base.shape), base), world
         rgb = backends[0].finalize(total).cpu().numpy().reshape(base.shape[0], base.shape[1], 3)
         assert np.array_equal(rgb, (base[..., :3] // base[..., 3:4]).astype(np.uint8))
+        assert np.array_equal(backends[0].finalize_to_host(total).reshape(rgb.shape), rgb)  # the pinned, recycled host frame
     # non-adaptive split
     _, base2, _ = dsc.render(cam, max_w, max_h, seed=22, adaptive=False, want_sums=True)
     world = 4
