@@ -237,6 +237,25 @@ def test_reference_sample_scenes_marshal_and_render_on_the_oracle(name):
         assert (prim == 3).sum() > 1000 and not (prim == 4).any()
 
 
+def test_output_frames_are_recycled_only_when_nobody_holds_them():
+    """native._frame_buffer: rt_render's output array is handed out again only once neither it nor a view of it is
+    referenced (so no caller ever sees a frame change under its feet)."""
+    shape = (7, 9, 3)
+    a = native._frame_buffer(shape)
+    b = native._frame_buffer(shape)
+    assert a is not b and a.shape == shape and a.dtype == np.uint8
+    row = a[2]          # a view keeps its base alive and unrecycled
+    ida = id(a)
+    del a
+    c = native._frame_buffer(shape)
+    assert id(c) != ida and c is not b
+    del row
+    d = native._frame_buffer(shape)
+    assert id(d) == ida  # released: recycled
+    held = [native._frame_buffer(shape) for _ in range(5)]  # more live frames than the ring keeps: all distinct
+    assert len({id(x) for x in held} | {id(b), id(c), id(d)}) == 8
+
+
 def test_marshal_preserves_texture_structure():
     interpret = Sphere.plane_map_inverse(2.0, (1.0, 2.0, 3.0))
     img = np.arange(4 * 6 * 3, dtype=np.uint8).reshape(4, 6, 3)
