@@ -5,10 +5,15 @@
     python bench.py --impl reference --gpus N ...            # the CPU arm: C++ restatement of the F# algorithm
 
 A step is one frame: Scene.render of the C2 scene (1201x801, 500 spp, depth 50, adaptive early-out as the
-reference does it).  `value` times the device-resident frame (probe + compact + main [+ all-reduces] +
-finalize) with CUDA events, L2 flushed between steps, max over ranks.  `e2e` times the public API with host
-buffers: Scene.make (BVH build + host->device upload) + Scene.render + Image.render (device->host image).
-Prints ONE JSON line on rank 0.
+reference does it).  Every frame is one library call, rt_comm_render: probe + [all-reduce of flags] + compact +
+main + [reduce-scatter of sums] + finalize + [all-gather of RGB8], kernels and NCCL collectives enqueued by
+librtfs_b200.so on the stream bench.py hands it.  `value` times the device-resident frame with CUDA events on that
+stream, L2 flushed between steps, max over ranks.  `e2e` times the public API with host buffers: Scene.make
+(marshal + BVH build + host->device upload) + Scene.render + Image.render (device->host image).  The line also
+carries: `roofline` (SURVEY 8d's algorithmic FLOPs of the reference traversal) and `roofline_useful` (the tests our
+traversal executed), `traversal`, `frame_sha256` (one fixed-seed frame hashed through every product path: equal
+for every N), `other_configs` (C1, C3, C4, the author's native 2401x1601 depth-150 frame, C5 at its full 4096 spp),
+`cpu_baseline`.  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -176,164 +181,269 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
+def executed_flops_per_ray(c, n_planes):
+    """SURVEY 8d's formula on the tests OUR traversal executed (RT_FLAG_COUNTERS): every ray tests every unbounded
+    object, so `n_planes` of the primitive tests per ray are plane tests (14 FLOP) and the rest sphere tests (20)."""
+    rays = max(1, c["rays"])
+    prim = c["prim_tests"] / rays
+    return 3.0 + 12.0 * c["box_tests"] / rays + 20.0 * max(0.0, prim - n_planes) + 14.0 * n_planes + 1.0 + 6.0
 
-    from ray_tracing_fsharp_b200 import abi, native
-    from ray_tracing_fsharp_b200.distributed import DeviceBackend, render_split_frame
+
+class Runner:
+    """One rank of the job: torch for the stream, the events, the barrier and the max-over-ranks; every frame is ONE
+    library call, rt_comm_render (kernels + NCCL collectives enqueued by librtfs_b200.so on the stream it is given)."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        from ray_tracing_fsharp_b200 import native
+        from ray_tracing_fsharp_b200.distributed import comm_from_torch_distributed
+        self.torch, self.dist, self.native, self.args = torch, dist, native, args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if native.device_count() < 1:
+            raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        self.ctl = None
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.ctl = dist.new_group(backend="gloo")  # host-side barrier for the phases where rank 0 drives every GPU itself
+        self.stream = torch.cuda.current_stream(self.dev)
+        self.comm = comm_from_torch_distributed(self.local_rank, self.stream.cuda_stream)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)  # > 126 MB L2
+        self.adaptive = not args.no_adaptive
+        self.flags = 0  # RtRenderOpts.flags of every frame
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def host_barrier(self):
+        self.torch.cuda.synchronize(self.dev)
+        if self.world > 1:
+            self.dist.barrier(group=self.ctl)
+
+    def reduce(self, values, op):
+        t = self.torch.tensor(values, dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=getattr(self.dist.ReduceOp, op))
+        return [float(x) for x in t.tolist()]
+
+    def scene(self, spec):
+        from ray_tracing_fsharp_b200.domain import marshal
+        from ray_tracing_fsharp_b200.scene import Camera
+        hs, ts, keep = marshal(spec.objects)
+        handle = self.native.SceneHandle(hs, ts, self.local_rank, keepalive=keep)
+        cam = Camera.make_basic(spec.spp, spec.focal_length, spec.aspect_ratio, spec.origin, spec.view_direction, spec.view_up)
+        cam.bounce_depth = spec.bounce_depth
+        return handle, cam
+
+    def enqueue(self, handle, cam, spec, seed, flags=None):
+        """One device-resident frame: nothing crosses PCIe, nothing synchronises."""
+        self.comm.render(handle, cam, spec.max_width_coord, spec.max_height_coord, seed=seed, adaptive=self.adaptive,
+                         flags=self.flags if flags is None else flags, want_rgb=False, want_sums=False, want_stats=False)
+
+    def measure(self, handle, cam, spec, steps, warmup, seed0=2000):
+        """W untimed frames, then K timed ones: L2 flushed, barrier + synchronize on both sides, CUDA events on the stream the
+        library enqueues on, max over ranks.  Returns whole-job totals plus rank 0's main-phase kernel figures."""
+        torch = self.torch
+        for i in range(warmup):
+            self.enqueue(handle, cam, spec, seed0 - 1000 + i)
+        self.barrier()
+        out = {"ms": 0.0, "rays": 0, "paths": 0, "launches": 0, "main_ms": [], "main_rays": [], "degenerate": 0}
+        for i in range(steps):
+            self.flush.fill_(i & 0xFF)
+            self.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(self.stream)
+            self.enqueue(handle, cam, spec, seed0 + i)
+            e1.record(self.stream)
+            self.barrier()
+            st = self.comm.last_stats(handle)  # this rank's counters and the events the library recorded around its kernels
+            ms, = self.reduce([e0.elapsed_time(e1)], "MAX")
+            rays, paths, launches, degenerate = self.reduce([st.rays, st.paths, st.launches, st.degenerate_paths], "SUM")
+            out["ms"] += ms
+            out["rays"] += int(rays)
+            out["paths"] += int(paths)
+            out["launches"] += int(launches)
+            out["degenerate"] += int(degenerate)
+            out["main_ms"].append(st.main_ms)
+            out["main_rays"].append(int(st.main_rays))
+        return out
+
+    def counters(self, handle, cam, spec, seed=4000):
+        """One untimed frame with RT_FLAG_COUNTERS (a slower kernel variant): the tests OUR traversal executes."""
+        from ray_tracing_fsharp_b200 import abi
+        _, _, st = self.comm.render(handle, cam, spec.max_width_coord, spec.max_height_coord, seed=seed, adaptive=self.adaptive,
+                                    flags=self.flags | abi.RT_FLAG_COUNTERS, want_rgb=False, want_sums=False, want_stats=True)
+        rays, paths, box, prim = self.reduce([st.rays, st.paths, st.box_tests, st.prim_tests], "SUM")
+        return {"rays": rays, "paths": paths, "box_tests": box, "prim_tests": prim}
+
+
+def n_planes_of(spec):
+    from ray_tracing_fsharp_b200.domain import Hittable
+    return sum(1 for o in spec.objects if isinstance(o, Hittable.InfinitePlane))
+
+
+def frame_hashes(r, handle, cam, spec, seed=424242):
+    """One extra untimed frame with a fixed seed through every product path; SHA-256 of the RGB8 frame and of the int32
+    PixelStats sums.  Equal hashes across N = 1, 2, 4, 8 and across the paths are the multi-GPU correctness evidence."""
+    import hashlib
+    from ray_tracing_fsharp_b200 import native
+    mw, mh = spec.max_width_coord, spec.max_height_coord
+    sha = lambda a: hashlib.sha256(a.tobytes()).hexdigest()  # noqa: E731
+    paths = {}
+    rgb, sums, _ = r.comm.render(handle, cam, mw, mh, seed=seed, adaptive=r.adaptive, flags=r.flags, want_rgb=True, want_sums=True)
+    ref_rgb, ref_sums = sha(rgb), sha(sums)
+    paths["rt_comm_render, sums all-reduced"] = ref_rgb
+    rgb2, _, _ = r.comm.render(handle, cam, mw, mh, seed=seed, adaptive=r.adaptive, flags=r.flags, want_rgb=True, want_sums=False)
+    paths["rt_comm_render, sums reduce-scattered + RGB8 all-gathered"] = sha(rgb2)
+    out = {"seed": seed, "rgb8": ref_rgb, "sums_int32": ref_sums}
+    r.host_barrier()
+    if r.rank == 0:
+        if r.world == 1:
+            rgb3, sums3, _ = handle.render(cam, mw, mh, seed=seed, adaptive=r.adaptive, flags=r.flags, want_sums=True)
+            paths["rt_render"] = sha(rgb3)
+            out["sums_int32_rt_render"] = sha(sums3)
+        elif native.device_count() >= r.world:
+            # one process (this one) driving all N devices through peer memory: what a single F# host process would call
+            from ray_tracing_fsharp_b200.domain import marshal
+            hs, ts, keep = marshal(spec.objects)
+            multi = native.MultiHandle(hs, ts, list(range(r.world)), keepalive=keep)
+            multi.render(cam, mw, mh, seed=seed - 1, adaptive=r.adaptive, flags=r.flags)  # first use: allocations
+            t0 = time.perf_counter()
+            rgb3, sums3, st3 = multi.render(cam, mw, mh, seed=seed, adaptive=r.adaptive, flags=r.flags, want_sums=True)
+            wall = time.perf_counter() - t0
+            paths["rt_multi_render (one process, peer memory)"] = sha(rgb3)
+            out["sums_int32_rt_multi_render"] = sha(sums3)
+            out["rt_multi_render"] = {"device_ms": st3.kernel_ms, "wall_ms_with_sums_copy": 1e3 * wall, "rays": int(st3.rays), "devices": r.world}
+            t0 = time.perf_counter()
+            rgb4, _, st4 = multi.render(cam, mw, mh, seed=seed, adaptive=r.adaptive, flags=r.flags)  # the call a host makes: frame into a host buffer
+            wall = time.perf_counter() - t0
+            out["rt_multi_render"].update({"wall_ms": 1e3 * wall, "mrays_per_s_wall": st4.rays / wall / 1e6})
+            paths["rt_multi_render, second call"] = sha(rgb4)
+            multi.close()
+    r.host_barrier()
+    out["paths"] = paths
+    out["all_paths_equal"] = len(set(paths.values())) == 1 and all(out.get(k, ref_sums) == ref_sums for k in ("sums_int32_rt_render", "sums_int32_rt_multi_render"))
+    return out
+
+
+def e2e_frames(r, spec, cam, n_e2e):
+    """The public API with HOST buffers, every step: Scene.make (marshal + BVH build + host->device upload of the scene) +
+    Scene.render + Image.render (kernels, collectives, device->host copy of the frame).  Wall clock, max over ranks."""
+    from ray_tracing_fsharp_b200 import native
     from ray_tracing_fsharp_b200.domain import marshal
-    from ray_tracing_fsharp_b200.scene import Camera, Image, Scene
+    from ray_tracing_fsharp_b200.scene import Image, Scene
+    mw, mh = spec.max_width_coord, spec.max_height_coord
+    secs, rays_total, h2d, d2h = 0.0, 0, 0, 0
+    for i in range(-2, n_e2e):  # two untimed iterations: first-use allocations (handle pool, recycled output frames)
+        r.barrier()
+        t0 = time.perf_counter()
+        if r.world == 1:
+            sc = Scene.make(spec.objects, device=r.local_rank)
+            _, image = Scene.render(lambda _p: None, lambda _s: None, mw, mh, cam, sc, seed=3000 + i, adaptive=r.adaptive, flags=r.flags)
+            pixels = Image.render(image)
+            rays = sc.last_stats.rays
+            h2d = sc.handle.device_bytes()
+            d2h = pixels.nbytes + 128
+            sc.handle.close()
+        else:
+            hs, ts, keep = marshal(spec.objects)
+            sc = native.SceneHandle(hs, ts, r.local_rank, keepalive=keep)
+            rgb, _, st = r.comm.render(sc, cam, mw, mh, seed=3000 + i, adaptive=r.adaptive, flags=r.flags, want_rgb=(r.rank == 0), want_stats=True)
+            rays = st.rays
+            h2d = sc.device_bytes()
+            d2h = (rgb.nbytes if rgb is not None else 0) + 128
+            sc.close()
+        r.barrier()
+        dt, = r.reduce([time.perf_counter() - t0], "MAX")
+        rr, h2d_all, d2h_all = r.reduce([rays, h2d, d2h], "SUM")
+        if i >= 0:
+            secs += dt
+            rays_total += int(rr)
+    return {"secs": secs, "rays": rays_total, "h2d": int(h2d_all), "d2h": int(d2h_all)}
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if native.device_count() < 1:
-        raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
+def other_config_specs(args):
+    from ray_tracing_fsharp_b200 import sample_images
+    out = []
+    for name in args.other_configs.split(","):
+        name = name.strip()
+        if not name or name == args.config:
+            continue
+        if name == "native":
+            # the author's own workload: randomSpheres at (1200, 800) half-extents, BounceDepth 150 as Camera.makeBasic sets it
+            # (RayTracing.App/SampleImages.fs:818-827, :960; Camera.fs:58)
+            spec = sample_images.random_spheres(max_w=1200, max_h=800, spp=500, depth=150)
+            spec.name = "RTOW final scene at the author's native size (random-spheres)"
+            out.append((name, spec, "C2", 2))
+        else:
+            out.append((name, sample_images.CONFIGS[name](), name, 1 if name == "C5" else 3))
+    return out
 
-    adaptive = not args.no_adaptive
+
+def run_ours(args):
+    from ray_tracing_fsharp_b200 import abi, native
+    r = Runner(args)
+    torch, rank, world = r.torch, r.rank, r.world
+    r.flags = abi.RT_FLAG_NO_SMEM if args.no_smem else 0
     spec = build_spec(args)
-    cam = Camera.make_basic(spec.spp, spec.focal_length, spec.aspect_ratio, spec.origin, spec.view_direction, spec.view_up)
-    cam.bounce_depth = spec.bounce_depth
-    max_w, max_h = spec.max_width_coord, spec.max_height_coord
-    hs, ts, keep = marshal(spec.objects)
-    scene = native.SceneHandle(hs, ts, local_rank, keepalive=keep)
-    flags = (abi.RT_FLAG_NO_SMEM if args.no_smem else 0)
-    backend = DeviceBackend(scene, cam, max_w, max_h, seed=1, adaptive=adaptive, flags=flags)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    handle, cam = r.scene(spec)
+    fp32_peak = native.measure_fp32_peak(r.local_rank) if rank == 0 else 0.0
 
-    def red_max(t):
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-
-    def red_sum(t):
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-
-    main_events = []
-
-    def frame(seed, time_main=False):
-        """probe -> [all-reduce flags] -> compact + main -> [all-reduce sums] -> finalize on rank 0 (distributed.py)."""
-        backend.opts.seed = seed
-        stats, flags = backend.alloc()
-        backend.probe(rank, world, stats, flags)
-        if world > 1:
-            red_max(flags)
-        if time_main:  # the dominant kernel, for the roofline: events on the stream the kernels are launched on
-            m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            m0.record()
-        backend.main(rank, world, stats, flags)
-        if time_main:
-            m1.record()
-            main_events.append((m0, m1))
-        if world > 1:
-            red_sum(stats)
-        return backend.finalize(stats) if rank == 0 else None
-
-    fp32_peak = native.measure_fp32_peak(local_rank) if rank == 0 else 0.0
-
-    for i in range(args.warmup):
-        frame(1000 + i)
-    barrier()
-
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(r.local_rank)
+    for i in range(args.warmup):  # warm-up outside the clock window
+        r.enqueue(handle, cam, spec, 1000 + i)
+    r.barrier()
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
     t_begin = time.perf_counter()
-    ms_total = 0.0
-    rays = paths = 0
-    launches0 = backend.launches
-    for i in range(args.steps):
-        flush.fill_(i & 0xFF)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        frame(2000 + i, time_main=True)
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        c = backend.counters()
-        work = torch.tensor([c.rays, c.paths], dtype=torch.int64, device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-            dist.all_reduce(work, op=dist.ReduceOp.SUM)
-        ms_total += float(ms.item())
-        rays += int(work[0].item())
-        paths += int(work[1].item())
+    m = r.measure(handle, cam, spec, args.steps, 0)
     t_end = time.perf_counter()
     clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
-    launches = backend.launches - launches0
-    launch_t = torch.tensor([launches], dtype=torch.int64, device=dev)
-    if world > 1:
-        dist.all_reduce(launch_t, op=dist.ReduceOp.SUM)
-    secs = ms_total / 1e3
-    value = rays / secs / 1e6
-    # the main-phase kernel alone (rank 0's launches): its share of the rays comes from an untimed probe-only frame
-    main_ms = sum(a.elapsed_time(b) for a, b in main_events) / max(1, len(main_events))
-    backend.opts.seed = 2000 + args.steps - 1
-    ps_, pf_ = backend.alloc()
-    backend.probe(rank, world, ps_, pf_)
-    probe_rays_rank0 = backend.counters().rays
-    if world > 1:
-        red_max(pf_)
-    backend.main(rank, world, ps_, pf_)
-    main_rays_rank0 = backend.counters().rays - probe_rays_rank0
+    secs = m["ms"] / 1e3
+    value = m["rays"] / secs / 1e6
+    main_ms = sum(m["main_ms"]) / max(1, len(m["main_ms"]))
+    main_rays = sum(m["main_rays"]) / max(1, len(m["main_rays"]))
 
-    # ---- end to end through the public API with host buffers ----
-    e2e_secs = 0.0
-    e2e_rays = 0
-    h2d = d2h = 0
     n_e2e = max(1, min(args.steps, 3))
-    for i in range(-2, n_e2e):  # two untimed warm-up iterations (first-use allocations: handle pool, the two recycled output frames)
-        barrier()
-        t0 = time.perf_counter()
-        if world == 1:
-            sc = Scene.make(spec.objects, device=local_rank)              # host BVH build + H2D upload of the scene
-            _, image = Scene.render(lambda _p: None, lambda _s: None, max_w, max_h, cam, sc, seed=3000 + i, adaptive=adaptive, flags=flags)
-            pixels = Image.render(image)                                  # kernels + D2H of the image
-            st = sc.last_stats
-            r_rays = st.rays
-            h2d = sc.handle.device_bytes()
-            d2h = pixels.nbytes + 64
-            sc.handle.close()
-        else:
-            hs2, ts2, keep2 = marshal(spec.objects)
-            sc2 = native.SceneHandle(hs2, ts2, local_rank, keepalive=keep2)
-            be = DeviceBackend(sc2, cam, max_w, max_h, seed=3000 + i, adaptive=adaptive, flags=flags)
-            stats_t, _ = render_split_frame(be, rank, world, red_max, red_sum)
-            if rank == 0:
-                pixels = be.finalize_to_host(stats_t)  # device->host copy of the frame into pinned host memory
-                d2h = pixels.nbytes + 64
-            torch.cuda.synchronize(dev)
-            r_rays = be.counters().rays
-            h2d = sc2.device_bytes()
-            sc2.close()
-        barrier()
-        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        rr = torch.tensor([r_rays], dtype=torch.int64, device=dev)
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-            dist.all_reduce(rr, op=dist.ReduceOp.SUM)
-        if i >= 0:
-            e2e_secs += float(dt.item())
-            e2e_rays += int(rr.item())
+    e2e = e2e_frames(r, spec, cam, n_e2e)
+    trav = r.counters(handle, cam, spec)
+    hashes = frame_hashes(r, handle, cam, spec) if not args.no_hash else None
 
-    # one extra, untimed frame with the traversal counters on (a slower kernel variant): tests per ray of OUR traversal
-    traversal = None
-    if args.counters:
-        be = DeviceBackend(scene, cam, max_w, max_h, seed=4000, adaptive=adaptive, flags=flags | abi.RT_FLAG_COUNTERS)
-        render_split_frame(be, rank, world, red_max, red_sum)
-        c = be.counters()
-        traversal = {"box_tests_per_ray": c.box_tests / max(1, c.rays), "prim_tests_per_ray": c.prim_tests / max(1, c.rays),
-                     "rays_per_path": c.rays / max(1, c.paths)}
+    # ---- the other BASELINE configs (and the author's native frame), each a short measurement of its own ----
+    others = {}
+    for name, ospec, fkey, osteps in ([] if args.no_other_configs else other_config_specs(args)):
+        oh, ocam = r.scene(ospec)
+        if name == "C5":  # a full-spp warm-up frame would cost as much as the measurement: warm up on a 16-spp frame
+            wcam = type(ocam).from_buffer_copy(ocam)
+            wcam.samples_per_pixel = 16
+            r.enqueue(oh, wcam, ospec, 900)
+            r.barrier()
+            om = r.measure(oh, ocam, ospec, osteps, 0, seed0=5000)
+        else:
+            om = r.measure(oh, ocam, ospec, osteps, 1, seed0=5000)
+        oc = r.counters(oh, ocam, ospec) if name != "C5" else None
+        o_main_ms = sum(om["main_ms"]) / len(om["main_ms"])
+        o_main_rays = sum(om["main_rays"]) / len(om["main_rays"])
+        f_ref = FLOPS_PER_RAY[fkey]
+        entry = {"workload": workload_name(ospec, r.adaptive), "steps": osteps, "ms_per_step": om["ms"] / osteps,
+                 "mrays_per_s": om["rays"] / (om["ms"] / 1e3) / 1e6, "mpaths_per_s": om["paths"] / (om["ms"] / 1e3) / 1e6,
+                 "rays_per_step": om["rays"] / osteps, "main_kernel_ms": o_main_ms,
+                 "flops_per_ray_reference_algorithm": f_ref,
+                 "frac": (o_main_rays / (o_main_ms / 1e3) * f_ref / 1e12 / fp32_peak) if (rank == 0 and fp32_peak and o_main_ms > 0) else None,
+                 "scene_bytes_staged_in_shared_memory": oh.shared_memory_bytes()}
+        if oc:
+            f_exec = executed_flops_per_ray(oc, n_planes_of(ospec))
+            entry["traversal"] = {"box_tests_per_ray": oc["box_tests"] / max(1, oc["rays"]), "prim_tests_per_ray": oc["prim_tests"] / max(1, oc["rays"])}
+            entry["frac_executed_tests"] = (o_main_rays / (o_main_ms / 1e3) * f_exec / 1e12 / fp32_peak) if (rank == 0 and fp32_peak and o_main_ms > 0) else None
+        others[name] = entry
+        oh.close()
 
     if rank == 0:
         cpu = None
@@ -343,47 +453,69 @@ def run_ours(args):
             cpu = {"value": s["counters"]["rays"] / s["seconds"] / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port",
                    "sample": f"every {s['row_step']}th row of the frame ({s['rows']} of {spec.rows} rows) at full spp, {s['seconds']:.1f} s",
                    "mpaths_per_s": s["counters"]["paths"] / s["seconds"] / 1e6, "counters": s["counters"]}
-        # algorithmic FLOPs per ray of the REFERENCE traversal on this scene: measured by the oracle on the CPU
-        # sample when it ran, else the figure recorded in DESIGN.md for C2
+        # algorithmic FLOPs per ray of the REFERENCE traversal on this scene (SURVEY 8d): measured by the oracle on the CPU
+        # sample when it ran, else the figure recorded in DESIGN.md for the config
         f_ray = flops_per_ray(cpu["counters"]) if cpu else (args.flops_per_ray or FLOPS_PER_RAY[args.config])
-        achieved = main_rays_rank0 / (main_ms / 1e3) * f_ray / 1e12
-        traffic = None
+        f_exec = executed_flops_per_ray(trav, n_planes_of(spec))
+        rate = main_rays / (main_ms / 1e3) if main_ms > 0 else 0.0
+        achieved, achieved_exec = rate * f_ray / 1e12, rate * f_exec / 1e12
+        traffic = l2_per_ray = hbm_per_ray = None
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tp) and args.config == "C2" and not args.spp and not args.half_extents:  # the ncu capture is of the C2 main kernel
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                tj = json.load(open(tp))
+                traffic = tj.get("dram_bytes_per_launch")
+                if tj.get("rays_per_launch"):
+                    hbm_per_ray = tj["dram_bytes_per_launch"] / tj["rays_per_launch"]
+                    l2_per_ray = tj.get("l2_bytes_per_launch", 0) / tj["rays_per_launch"] or None
             except Exception:
                 traffic = None
         line = {
             "metric": metric_name(spec, args.config),
-            "value": value, "unit": "Mrays/s", "mpaths_per_s": paths / secs / 1e6,
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "value": value, "unit": "Mrays/s", "mpaths_per_s": m["paths"] / secs / 1e6,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["ms"] / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(spec, adaptive), "l2": "flushed between steps (256 MiB fill)",
-                       "parallelism": f"sample-split x{world}" + (", NCCL all-reduce of flags (max) and sums (int32 sum)" if world > 1 else ""),
-                       "scene_bytes_staged_in_shared_memory": 0 if args.no_smem else scene.shared_memory_bytes()},
-            "rays_per_step": rays / args.steps, "paths_per_step": paths / args.steps,
-            "e2e": {"value": e2e_rays / e2e_secs / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": 1e3 * e2e_secs / n_e2e, "steps": n_e2e,
-                    "what": ("Scene.make (BVH build + upload) + Scene.render + Image.render with host buffers" if world == 1 else
-                             "per rank: marshal + rt_scene_create (BVH build + upload) + rt_device_probe / all-reduce / rt_device_main / all-reduce; "
-                             "rank 0: rt_device_finalize + device->host copy of the frame into pinned host memory")},
-            "gpu_launches": int(launch_t.item()),
+            "config": {"workload": workload_name(spec, r.adaptive), "l2": "flushed between steps (256 MiB fill)",
+                       "parallelism": f"sample-split x{world}" + (", collectives issued by librtfs_b200.so (rt_comm_render): NCCL all-reduce of flags (uint8 max), "
+                                                                    "reduce-scatter of sums (int32), all-gather of RGB8" if world > 1 else ""),
+                       "scene_bytes_staged_in_shared_memory": 0 if args.no_smem else handle.shared_memory_bytes()},
+            "rays_per_step": m["rays"] / args.steps, "paths_per_step": m["paths"] / args.steps, "degenerate_paths": m["degenerate"],
+            "e2e": {"value": e2e["rays"] / e2e["secs"] / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+                    "ms_per_step": 1e3 * e2e["secs"] / n_e2e, "steps": n_e2e,
+                    "what": ("Scene.make (marshal + BVH build + upload) + Scene.render + Image.render with host buffers" if world == 1 else
+                             "per rank: marshal + rt_scene_create (BVH build + upload) + rt_comm_render (kernels and NCCL collectives inside the library); "
+                             "rank 0 receives the frame in a host buffer; bytes are summed over ranks")},
+            "gpu_launches": m["launches"],
             "clocks": clocks,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak if fp32_peak else None,
                          "traffic": traffic, "flops_per_ray": f_ray,
-                         "kernel": "render_kernel<PROBE=0> (main phase), rank 0", "kernel_ms_per_launch": main_ms, "rays_per_launch": main_rays_rank0,
-                         "note": "achieved = rays per launch x FLOPs the REFERENCE traversal spends per ray (exhaustive DFS, SURVEY 8d) / CUDA-event "
-                                 "duration of the launch; peak = FP32 FMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP32 "
-                                 "figure); traffic = DRAM bytes per launch, ncu, profiles/roofline_traffic.json"},
+                         "kernel": "render_kernel<PROBE=0> (main phase), rank 0", "kernel_ms_per_launch": main_ms, "rays_per_launch": main_rays,
+                         "hbm_bytes_per_ray": hbm_per_ray, "l2_bytes_per_ray": l2_per_ray,
+                         "note": "achieved = rays per launch x FLOPs the REFERENCE traversal spends per ray (exhaustive DFS, SURVEY 8d: the contract's "
+                                 "algorithmic figure) / duration of the launch from CUDA events the library records around it on its stream; the tests "
+                                 "the device actually executes are under roofline_useful; peak = FP32 FMA microbenchmark measured in this run "
+                                 "(MEASURED_PEAKS.json has no FP32 figure); traffic, hbm/l2 bytes per ray = ncu, profiles/roofline_traffic.json"},
+            "roofline_useful": {"bound": "fp32", "achieved": achieved_exec, "peak": fp32_peak, "unit": "TFLOP/s",
+                                "frac": achieved_exec / fp32_peak if fp32_peak else None, "flops_per_ray": f_exec,
+                                "note": "the same launch counted with the slab / primitive tests OUR ordered, culled traversal executed "
+                                        "(RT_FLAG_COUNTERS frame), SURVEY 8d's per-test weights; shading, RNG and control flow are not counted"},
+            "traversal": {"box_tests_per_ray": trav["box_tests"] / max(1, trav["rays"]), "prim_tests_per_ray": trav["prim_tests"] / max(1, trav["rays"]),
+                          "rays_per_path": trav["rays"] / max(1, trav["paths"])},
         }
-        if traversal:
-            line["traversal"] = traversal
+        if hashes:
+            line["frame_sha256"] = hashes
+        if others:
+            line["other_configs"] = others
+        if world > 1:
+            v, path = native.CommHandle.nccl_version()
+            line["config"]["nccl"] = f"{v} bound by librtfs_b200.so from {path}"
         if cpu:
             line["cpu_baseline"] = {k: v for k, v in cpu.items() if k != "counters"}
         print(json.dumps(line), flush=True)
+    handle.close()
+    r.comm.close()
     if world > 1:
-        dist.destroy_process_group()
+        r.dist.destroy_process_group()
     return 0
 
 
@@ -399,7 +531,9 @@ def main():
     ap.add_argument("--no-adaptive", action="store_true")
     ap.add_argument("--no-smem", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--counters", action="store_true", help="also report box / primitive tests per ray of the device traversal")
+    ap.add_argument("--no-hash", action="store_true", help="skip the fixed-seed frame hashed through every product path")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the short measurements of the other BASELINE configs")
+    ap.add_argument("--other-configs", default="C1,C3,C4,native,C5", help="which of C1..C5 / native to measure after the headline config")
     ap.add_argument("--cpu-seconds", type=float, default=25.0)
     ap.add_argument("--flops-per-ray", type=float, default=0.0, help="FLOPs of the reference traversal per ray, used when the CPU sample does not run (default: the config's figure from DESIGN.md)")
     args = ap.parse_args()

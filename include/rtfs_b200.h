@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define RT_ABI_VERSION 1
+#define RT_ABI_VERSION 2
 
 /* ---- error codes --------------------------------------------------------------------------- */
 #define RT_OK 0
@@ -140,6 +140,10 @@ typedef struct RtStats {
     uint64_t pixels_early_out;
     int32_t launches;   /* kernels launched by this call                                         */
     int32_t _pad0;
+    double main_ms;     /* device time of the main-phase kernel alone (compact + render_kernel<PROBE=0>) */
+    uint64_t main_rays; /* hitObject calls of that launch (this rank's)                          */
+    uint64_t degenerate_paths; /* paths ended where the reference would throw (Ray.make' / ValueOption.get failing):
+                                  rendered Black, counted here; 0 on non-degenerate scenes        */
 } RtStats;
 
 typedef struct RtScene RtScene;
@@ -248,6 +252,42 @@ int rt_device_counters(RtScene *scene, void *stream, RtStats *stats);
  * all-reduce) -> d_rgb rows*cols*3. */
 int rt_device_finalize(int32_t device, const int32_t *d_stats, int32_t n_pixels, int32_t gamma,
                        uint8_t *d_rgb, void *stream);
+
+/* ---- render (one process per GPU; the collectives are issued by the library) -------------------- */
+/* The sample-split frame of SURVEY.md 8e for a job of `world` processes, one per GPU, each holding a replica of
+ * the scene: rank r probes its share of the tiles (Scene.fs:172-188), the flags are all-reduced (MAX), rank r
+ * adds its share of the remaining sample indices (Scene.fs:191-192), the PixelStats sums are reduce-scattered
+ * (int32 SUM) so that every rank divides (Pixel.fs:103-108) and gamma-corrects (ImageOutput.fs:11-18) one slice
+ * of the pixels, and the RGB8 slices are all-gathered.  All of it — kernels and NCCL calls — is enqueued by
+ * rt_comm_render on one stream; the image is bit-identical to rt_render's for every world size.
+ * NCCL (libnccl.so.2) is bound at run time on first use: RT_ERR_UNSUPPORTED if it cannot be loaded.
+ *
+ * Bootstrap as with NCCL itself: one rank calls rt_comm_unique_id, the host program hands the 128 bytes to every
+ * rank (the F# host: a file, a pipe or MPI; bench.py: torch.distributed's store), every rank calls rt_comm_create
+ * (collective).  `stream`: the cudaStream_t to enqueue on, or NULL for a stream owned by the communicator. */
+#define RT_COMM_ID_BYTES 128
+typedef struct RtComm RtComm;
+int rt_comm_unique_id(uint8_t *id_out /* RT_COMM_ID_BYTES */);
+int rt_comm_create(const uint8_t *id, int32_t rank, int32_t world, int32_t device, void *stream,
+                   RtComm **out);
+void rt_comm_destroy(RtComm *comm);
+/* version (e.g. 22809) and file name of the NCCL build the library bound */
+int rt_comm_nccl_version(int32_t *version_out, char *path_out, size_t path_cap);
+/* One frame (collective: every rank calls it with the same camera, extents and opts, on its own replica of the
+ * scene).  rgb_out / sums_out: host buffers as for rt_render, or NULL on ranks that do not want them (the
+ * frame is complete in device memory on every rank either way; passing sums_out makes the ranks all-reduce the
+ * sums instead of reduce-scattering them).  stats: THIS rank's paths and rays.  With rgb_out, sums_out and
+ * stats all NULL the call only enqueues work and returns without synchronising (device-resident use). */
+int rt_comm_render(RtComm *comm, RtScene *scene, const RtCamera *camera, int32_t max_width_coord,
+                   int32_t max_height_coord, const RtRenderOpts *opts, uint8_t *rgb_out,
+                   int32_t *sums_out, RtStats *stats);
+/* Timing and work counters of the last rt_comm_render that was enqueued with rgb_out, sums_out and stats all
+ * NULL, once the caller has synchronised the stream: kernel_ms, main_ms, total_ms from the events the call
+ * recorded; paths, rays, main_rays from counter snapshots it copied to pinned memory. */
+int rt_comm_last_stats(RtComm *comm, RtScene *scene, RtStats *stats);
+/* device pointers of the last frame: RGB8 rows*cols*3, and the sum buffer (complete only after a call with
+ * sums_out or world == 1; otherwise only this rank's slice holds totals).  Valid until the next call. */
+int rt_comm_frame(RtComm *comm, const uint8_t **d_rgb_out, const int32_t **d_stats_out);
 
 /* ---- per-primitive conformance entry points (device) ---------------------------------------- */
 /* Each runs one thread per vector through exactly the __device__ function the render kernels call.

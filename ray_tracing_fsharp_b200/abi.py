@@ -5,7 +5,7 @@ struct against the values the compiled library reports.
 """
 import ctypes as C
 
-RT_ABI_VERSION = 1
+RT_ABI_VERSION = 2
 
 RT_OK = 0
 RT_ERR_INVALID_ARGUMENT = -1
@@ -39,6 +39,8 @@ RT_MODE_WAVEFRONT = 1
 
 RT_FLAG_COUNTERS = 1
 RT_FLAG_NO_SMEM = 2
+
+RT_COMM_ID_BYTES = 128
 
 RT_BVH_SAH = 0
 RT_BVH_REFERENCE = 1
@@ -113,4 +115,7 @@ class RtStats(C.Structure):
         ("pixels_early_out", C.c_uint64),
         ("launches", C.c_int32),
         ("_pad0", C.c_int32),
+        ("main_ms", C.c_double),
+        ("main_rays", C.c_uint64),
+        ("degenerate_paths", C.c_uint64),
     ]

@@ -27,6 +27,7 @@ namespace rtfs {
 constexpr float kTolF = 1e-8f;   // Float.tolerance, RayTracing/Float.fs:80
 constexpr double kTolD = 1e-8;
 constexpr uint32_t kWhite = 0x00FFFFFFu, kBlack = 0u, kHotPink = (205u << 16) | (105u << 8) | 180u; // Pixel.fs:18-66
+constexpr uint32_t kDegenerate = 0x80000000u; // flag on a path's result: it ended where the reference would throw (rendered Black)
 constexpr int kNoPrim = -1;
 constexpr int kNoRef = 0x7fffffff; // "no primitive" where primitives are named by ref (see SceneAccess)
 constexpr float kNoHitT = 3.402823466e38f; // "bestFloat = infinity" (Scene.fs:65) as the largest finite float
@@ -864,8 +865,8 @@ RTFS_HD bool path_after_hit(PathState &p, const SceneAccess<SMEM> &sc, const Hit
         result = p.colour;
         return true;
     }
-    if (r == SCATTER_ERROR) { // the reference throws here; unreachable on non-degenerate input
-        result = kBlack;
+    if (r == SCATTER_ERROR) { // the reference throws here; unreachable on non-degenerate input: Black, and counted
+        result = kBlack | kDegenerate;
         return true;
     }
     p.last = h.ref;

@@ -55,7 +55,7 @@ int workspace_acquire(int device, DeviceWorkspace **out) {
         ws->sm_count = prop.multiProcessorCount;
         ws->smem_optin = prop.sharedMemPerBlockOptin;
         ok = cudaMalloc((void **)&ws->d_counters, CN_SLOTS * sizeof(unsigned long long)) == cudaSuccess &&
-             cudaMallocHost((void **)&ws->h_counters, CN_SLOTS * sizeof(unsigned long long)) == cudaSuccess &&
+             cudaMallocHost((void **)&ws->h_counters, 2 * CN_SLOTS * sizeof(unsigned long long)) == cudaSuccess &&
              cudaStreamCreateWithFlags(&ws->stream, cudaStreamNonBlocking) == cudaSuccess;
         for (auto &e : ws->ev) ok = ok && cudaEventCreate(&e) == cudaSuccess;
     }
@@ -119,6 +119,7 @@ static void texture_release(const PooledTexture &t) {
         g_texture_pool.push_back(t);
         return;
     }
+    cudaSetDevice(t.device);
     cudaDestroyTextureObject(t.object);
     cudaFreeArray(t.array);
 }
@@ -130,10 +131,13 @@ void device_scene_free(RtScene *scene) {
     auto *ds = static_cast<DeviceScene *>(scene->dev);
     if (!ds) return;
     cudaSetDevice(ds->device);
-    if (ds->ws) workspace_release(ds->ws); // synchronises the stream first: nothing is still reading the scene
-    for (const PooledTexture &t : ds->images) texture_release(t);
+    // rt_device_probe / rt_device_main / rt_comm_render launch on the caller's stream, not the workspace's: quiesce the whole
+    // device before the workspace and the texture arrays go back to pools another handle may draw from at once
+    cudaDeviceSynchronize();
     cudaFree(ds->ref_nodes);
     cudaFree(ds->blob);
+    if (ds->ws) workspace_release(ds->ws);
+    for (const PooledTexture &t : ds->images) texture_release(t);
     delete ds;
     scene->dev = nullptr;
 }
@@ -394,6 +398,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) render_kernel(const FramePar
                         uint32_t sample = uint32_t(PROBE ? j_begin + j : fp.sample_begin + fp.rank + (j_begin + j) * fp.world);
                         ++n_paths;
                         active = path_begin(ps, fp.cam, fp.k0, fp.k1, rc >> 16, rc & 0xffff, sample); // false: Ray.make' failed (the reference throws)
+                        if (!active) atomicAdd(fp.counters + CN_DEGENERATE, 1ull);
                     }
                 }
             }
@@ -439,6 +444,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) render_kernel(const FramePar
                     atomicAdd(acc + lane_slot, int((result >> 16) & 255u));
                     atomicAdd(acc + 32 + lane_slot, int((result >> 8) & 255u));
                     atomicAdd(acc + 64 + lane_slot, int(result & 255u));
+                    if (result & kDegenerate) atomicAdd(fp.counters + CN_DEGENERATE, 1ull);
                     active = false;
                 }
             }
@@ -719,6 +725,7 @@ void read_counters(DeviceScene *ds, RtStats *stats, size_t n_pixels, bool adapti
     stats->box_tests = ds->ws->h_counters[CN_BOX];
     stats->prim_tests = ds->ws->h_counters[CN_PRIM];
     stats->pixels_early_out = adaptive ? (unsigned long long)n_pixels - ds->ws->h_counters[CN_LIST] : 0;
+    stats->degenerate_paths = ds->ws->h_counters[CN_DEGENERATE];
 }
 
 // implemented in rtfs_wavefront.cu
@@ -878,8 +885,11 @@ int rt_render(RtScene *scene, const RtCamera *camera, int32_t max_w, int32_t max
     } else {
         RT_CUDA(cudaMemsetAsync(ds->ws->d_flags, 1, n_pixels, st));
     }
+    RT_CUDA(cudaMemcpyAsync(ds->ws->h_counters + CN_SLOTS, ds->ws->d_counters, CN_SLOTS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    RT_CUDA(cudaEventRecord(ds->ws->ev[4], st));
     rc = launch_main(ds, fp, single_flags(ds->ws->d_flags), count, no_smem, st, &launches);
     if (rc != RT_OK) return rc;
+    RT_CUDA(cudaEventRecord(ds->ws->ev[5], st));
     RT_CUDA(cudaEventRecord(ds->ws->ev[2], st));
     finalize_kernel<<<unsigned((n_pixels + 255) / 256), 256, 0, st>>>(ds->ws->d_stats, int(n_pixels), opts->gamma, ds->ws->d_rgb);
     RT_CUDA(cudaGetLastError());
@@ -897,6 +907,9 @@ int rt_render(RtScene *scene, const RtCamera *camera, int32_t max_w, int32_t max
         stats->kernel_ms = ms;
         cudaEventElapsedTime(&ms, ds->ws->ev[0], ds->ws->ev[3]);
         stats->total_ms = ms;
+        cudaEventElapsedTime(&ms, ds->ws->ev[4], ds->ws->ev[5]);
+        stats->main_ms = ms;
+        stats->main_rays = ds->ws->h_counters[CN_RAYS] - ds->ws->h_counters[CN_SLOTS + CN_RAYS];
         stats->launches = launches;
     }
     return RT_OK;

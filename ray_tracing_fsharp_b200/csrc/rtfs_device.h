@@ -32,7 +32,9 @@ inline int require_device(int device) {
 // ---------------------------------------------------------------------------------------------------
 // device scene
 // ---------------------------------------------------------------------------------------------------
-enum CounterSlot { CN_PATHS = 0, CN_RAYS = 1, CN_BOX = 2, CN_PRIM = 3, CN_LIST = 4, CN_WORK_PROBE = 5, CN_WORK_MAIN = 6, CN_SLOTS = 8 };
+enum CounterSlot { CN_PATHS = 0, CN_RAYS = 1, CN_BOX = 2, CN_PRIM = 3, CN_LIST = 4, CN_WORK_PROBE = 5, CN_WORK_MAIN = 6, CN_DEGENERATE = 7, CN_SLOTS = 16 };
+// (the last slot of the pinned copy is a scratch word of the wavefront driver; the pinned buffer holds a second set of
+// CN_SLOTS words: the snapshot taken between the probe and the main phase)
 
 // Frame buffers, scratch, stream and events of one device.  Allocating these costs milliseconds, so they are
 // pooled: a scene handle borrows one for its lifetime and returns it on destroy (handles stay independent of
@@ -52,7 +54,7 @@ struct DeviceWorkspace {
     unsigned long long *d_counters = nullptr;
     unsigned long long *h_counters = nullptr; // pinned
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // begin, zeroed, traced, end, main begin, main end
 };
 int workspace_acquire(int device, DeviceWorkspace **out);
 void workspace_release(DeviceWorkspace *ws);

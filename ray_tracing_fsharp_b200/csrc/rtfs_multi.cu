@@ -292,6 +292,7 @@ int rt_multi_render(RtMulti *m, const RtCamera *camera, int32_t max_w, int32_t m
             stats->rays += ds->ws->h_counters[CN_RAYS];
             stats->box_tests += ds->ws->h_counters[CN_BOX];
             stats->prim_tests += ds->ws->h_counters[CN_PRIM];
+            stats->degenerate_paths += ds->ws->h_counters[CN_DEGENERATE];
             listed = ds->ws->h_counters[CN_LIST];
             stats->launches += launches[i];
             float ms = 0.f;

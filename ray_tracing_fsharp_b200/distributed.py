@@ -6,9 +6,13 @@
              all_reduce(stats, SUM)   int32 {sumR, sumG, sumB, count} per pixel      [only if world > 1]
     tail     rt_device_finalize  PixelStats.mean (+ gamma) -> RGB8                   (Pixel.fs:103-108)
 
-Integer sums keyed by sample index make the result independent of `world`.  The orchestration below is
-backend-agnostic: the product backend (`DeviceBackend`) runs the CUDA kernels on torch CUDA tensors and
-NCCL; tests/ drive the same function with a CPU backend over gloo to check the decomposition.
+Integer sums keyed by sample index make the result independent of `world`.
+
+The PRODUCT form of this sequence is one library call, `rt_comm_render` (csrc/rtfs_comm.cu): kernels and NCCL
+collectives enqueued by the library on one stream (`native.CommHandle`; `comm_from_torch_distributed` below only
+carries the 128-byte NCCL id from rank 0 to the others).  `render_split_frame` spells the same steps out phase by
+phase over a backend: tests/ drive it with a CPU backend over gloo to check the decomposition, and with
+`DeviceBackend` (rt_device_probe / rt_device_main on torch tensors) to emulate several ranks on one GPU.
 """
 import ctypes as C
 
@@ -26,6 +30,19 @@ def render_split_frame(backend, rank: int, world: int, all_reduce_max=None, all_
     if world > 1:
         all_reduce_sum(stats)
     return stats, flags
+
+
+def comm_from_torch_distributed(device_index: int, stream=None) -> native.CommHandle:
+    """This process's rank of the library's communicator, bootstrapped over an initialised torch.distributed group
+    (any backend): rank 0 draws the NCCL id, broadcast_object_list carries it, every rank joins.  Without a process
+    group (or world 1) the communicator is a single rank and NCCL is never loaded."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return native.CommHandle(None, 0, 1, device_index, stream)
+    rank, world = dist.get_rank(), dist.get_world_size()
+    box = [native.CommHandle.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    return native.CommHandle(box[0], rank, world, device_index, stream)
 
 
 class DeviceBackend:

@@ -55,6 +55,13 @@ def _declare(lib):
                                      C.POINTER(RtStats)]),
         "rt_device_counters": (C.c_int, [_vp, _vp, C.POINTER(RtStats)]),
         "rt_device_finalize": (C.c_int, [_i32, _vp, _i32, _i32, _vp, _vp]),
+        "rt_comm_unique_id": (C.c_int, [_vp]),
+        "rt_comm_create": (C.c_int, [_vp, _i32, _i32, _i32, _vp, C.POINTER(_vp)]),
+        "rt_comm_destroy": (None, [_vp]),
+        "rt_comm_nccl_version": (C.c_int, [C.POINTER(_i32), C.c_char_p, C.c_size_t]),
+        "rt_comm_render": (C.c_int, [_vp, _vp, C.POINTER(RtCamera), _i32, _i32, C.POINTER(RtRenderOpts), _vp, _vp, C.POINTER(RtStats)]),
+        "rt_comm_last_stats": (C.c_int, [_vp, _vp, C.POINTER(RtStats)]),
+        "rt_comm_frame": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
         "rt_test_sphere_hit": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp]),
         "rt_test_plane_hit": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp]),
         "rt_test_aabb_hit": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _vp]),
@@ -261,6 +268,83 @@ class MultiHandle:
         stats = RtStats()
         check(lib().rt_multi_render(self.ptr, C.byref(camera), max_w, max_h, C.byref(opts), ptr(rgb), ptr(sums), C.byref(stats)))
         return rgb, sums, stats
+
+
+class CommHandle:
+    """Owner of an RtComm* (rt_comm_create / rt_comm_destroy): this process's rank of a one-process-per-GPU job whose
+    collectives the library issues itself (NCCL, bound at run time).  Creation is collective over the ranks."""
+
+    @staticmethod
+    def _torch_first():
+        """The library binds whatever libnccl.so.2 the process already holds, else the system's.  A process that will
+        ALSO import PyTorch must import it first: PyTorch needs the (newer) NCCL build it bundles, and the dynamic loader
+        keeps a single library per soname — binding the system's copy first makes `import torch` fail afterwards."""
+        import importlib.util
+        import sys
+        if "torch" not in sys.modules and importlib.util.find_spec("torch") is not None:
+            import torch  # noqa: F401
+
+    @staticmethod
+    def unique_id() -> bytes:
+        CommHandle._torch_first()
+        buf = (C.c_uint8 * abi.RT_COMM_ID_BYTES)()
+        check(lib().rt_comm_unique_id(buf))
+        return bytes(buf)
+
+    @staticmethod
+    def nccl_version():
+        CommHandle._torch_first()
+        v = _i32()
+        path = C.create_string_buffer(512)
+        check(lib().rt_comm_nccl_version(C.byref(v), path, 512))
+        return int(v.value), path.value.decode("utf-8", "replace")
+
+    def __init__(self, unique_id: bytes, rank: int, world: int, device: int, stream=None):
+        if unique_id is None and world == 1:
+            unique_id = bytes(abi.RT_COMM_ID_BYTES)
+        if len(unique_id) != abi.RT_COMM_ID_BYTES:
+            raise ValueError("unique_id must be RT_COMM_ID_BYTES long")
+        if world > 1:
+            CommHandle._torch_first()
+        self.rank, self.world, self.device = rank, world, device
+        idb = (C.c_uint8 * abi.RT_COMM_ID_BYTES).from_buffer_copy(unique_id)  # ignored by the library when world == 1
+        out = C.c_void_p()
+        check(lib().rt_comm_create(idb, rank, world, device, C.c_void_p(stream) if stream else None, C.byref(out)))
+        self.ptr = out
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            lib().rt_comm_destroy(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def render(self, scene: "SceneHandle", camera, max_w, max_h, seed=0, adaptive=True, gamma=False, flags=0, want_rgb=True,
+               want_sums=False, want_stats=True, rgb_out=None):
+        """One frame, collectively.  want_rgb / want_sums / want_stats all False: enqueue only (device-resident)."""
+        rows, cols = 2 * max_h + 1, 2 * max_w + 1
+        rgb = (rgb_out if rgb_out is not None else _frame_buffer((rows, cols, 3))) if want_rgb else None
+        sums = np.empty((rows, cols, 4), np.int32) if want_sums else None
+        opts = RtRenderOpts(seed, int(adaptive), abi.RT_MODE_MEGAKERNEL, int(gamma), flags)
+        stats = RtStats() if (want_stats or want_rgb or want_sums) else None
+        check(lib().rt_comm_render(self.ptr, scene.ptr, C.byref(camera), max_w, max_h, C.byref(opts), ptr(rgb), ptr(sums),
+                                   C.byref(stats) if stats is not None else None))
+        return rgb, sums, stats
+
+    def last_stats(self, scene: "SceneHandle"):
+        """Timing / counters of the last enqueue-only render (call after synchronising the stream)."""
+        stats = RtStats()
+        check(lib().rt_comm_last_stats(self.ptr, scene.ptr, C.byref(stats)))
+        return stats
+
+    def frame_pointers(self):
+        rgb, stats = C.c_void_p(), C.c_void_p()
+        check(lib().rt_comm_frame(self.ptr, C.byref(rgb), C.byref(stats)))
+        return rgb.value, stats.value
 
 
 # ---- free-standing conformance wrappers ---------------------------------------------------------

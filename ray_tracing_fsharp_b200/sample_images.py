@@ -3,11 +3,14 @@ sample scenes (REFERENCE_SAMPLES; `random-spheres` and `earth` are C2 and C3), b
 F# surface in domain.py.  They follow RayTracing.App/SampleImages.fs where a sample exists
 (randomSpheres :812-960, earth :962-1010, glassSphere :506-597, movedCamera :710-810) but draw their
 random parameters from a fixed-seed numpy generator instead of `System.Random ()`, so the oracle
-and the GPU are fed identical scenes.  No file under /root/reference is read.
+and the GPU are fed identical scenes.  No file under /root/reference is read (the earth map comes from a committed
+fixture, see load_earthmap).
 
 Each function returns a `SceneSpec`: objects, camera arguments (for Camera.makeBasic), the two
 half-extents handed to Scene.render (F6: image is (2*max_w+1) x (2*max_h+1)), spp and depth.
 """
+import functools
+import os
 from dataclasses import dataclass
 from typing import Any, List, Tuple
 
@@ -125,10 +128,36 @@ def synthetic_earthmap(width=1024, height=512, seed=7) -> np.ndarray:
     return np.clip(img, 0, 255).astype(np.uint8)
 
 
+# earthmap.jpg (the embedded resource LoadImage.fromResource decodes, RayTracing.App/LoadImage.fs:9-18) decoded once with
+# PIL / libjpeg-turbo by tests/golden/make_golden.py and committed losslessly: nothing here reads /root/reference
+_EARTHMAP_FIXTURE = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "earthmap_rgb8.png")
+
+
+@functools.lru_cache(maxsize=1)
+def load_earthmap():
+    """The bitmap `earth` textures its sphere with (SampleImages.fs:962-968), as [H, W, 3] uint8 with row 0 the top row of
+    the picture — what SKBitmap.GetPixel(x, y) indexes — plus a word saying what it is:
+      "earthmap.jpg decoded with PIL (committed fixture)"   the reference's own JPEG, decoded in the build container and
+                                           committed as a PNG, so that this container and the GPU box render the same texels;
+      "synthetic 1024x512 lat-long map"    the deterministic stand-in, when the fixture (or PIL) is missing.
+    Decoded texels are INPUT to the library (the decoder stays on the host side of the ABI): Skia's decoder
+    may differ from libjpeg-turbo's by a level or two per texel, which is outside the contract."""
+    try:
+        from PIL import Image as PilImage
+        if os.path.exists(_EARTHMAP_FIXTURE):
+            with PilImage.open(_EARTHMAP_FIXTURE) as im:
+                return np.ascontiguousarray(np.asarray(im.convert("RGB"), dtype=np.uint8)), "earthmap.jpg decoded with PIL (committed fixture)"
+    except Exception:  # PIL missing or the file unreadable: fall through to the stand-in
+        pass
+    return synthetic_earthmap(), "synthetic 1024x512 lat-long map"
+
+
 def earth(max_w=960, max_h=540, spp=256, depth=50, bitmap=None) -> SceneSpec:
-    """C3: `earth` (SampleImages.fs:962-1010) plus the two InfinitePlanes the config asks for."""
+    """C3: `earth` (SampleImages.fs:962-1010) plus the two InfinitePlanes the config asks for.  `bitmap`: the decoded
+    picture, row 0 on top (default: load_earthmap(), i.e. the reference's earthmap.jpg wherever it can be read)."""
+    source = "caller's bitmap"
     if bitmap is None:
-        bitmap = synthetic_earthmap()
+        bitmap, source = load_earthmap()
     texture = ParameterisedTexture.of_image(bitmap)
     interpret = Sphere.plane_map_inverse(1.0, (0.0, 0.0, 0.0))
     inv_sqrt2 = 1.0 / np.sqrt(2.0)
@@ -143,7 +172,7 @@ def earth(max_w=960, max_h=540, spp=256, depth=50, bitmap=None) -> SceneSpec:
         Hittable.InfinitePlane(InfinitePlane.make(InfinitePlaneStyle.PureReflection(0.9, Pixel(230, 230, 240)),
                                                   (-3.0, 0.0, 3.0), (inv_sqrt2, 0.0, -inv_sqrt2))),
     ]
-    return SceneSpec("C3 earthmap image-textured sphere + planes", objs, spp, 12.0, 16.0 / 9.0, (13.0, 2.0, -3.0),
+    return SceneSpec(f"C3 earthmap image-textured sphere + planes [{source}]", objs, spp, 12.0, 16.0 / 9.0, (13.0, 2.0, -3.0),
                      (0.0, 0.0, 0.0), (0.0, 1.0, 0.0), max_w, max_h, depth)
 
 

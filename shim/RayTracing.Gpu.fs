@@ -105,6 +105,9 @@ module internal Native =
         val mutable pixelsEarlyOut : uint64
         val mutable launches : int
         val mutable pad0 : int
+        val mutable mainMs : float
+        val mutable mainRays : uint64
+        val mutable degeneratePaths : uint64
 
     [<DllImport(Lib)>]
     extern nativeint rt_last_error ()

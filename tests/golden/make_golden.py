@@ -3,6 +3,9 @@
 
   PpmOutputExample.txt  <- RayTracing.Test/PpmOutputExample.txt, the P3 golden file of TestPpmOutput.fs:12-46
                            (the only golden-output fixture the reference holds for this path)
+  earthmap_rgb8.png     <- RayTracing.App/earthmap.jpg (the resource LoadImage.fromResource decodes, LoadImage.fs:9-18) decoded
+                           with PIL / libjpeg-turbo and stored losslessly: the texels the `earth` scene (C3) is rendered
+                           with, here and on the GPU box.  Decoded texels are input to the library, not reference code.
   oracle_frames.npz     <- small frames of the four scene families rendered by the CPU oracle (regression fixtures of
                            the oracle, not outputs of the F# reference)
 """
@@ -15,6 +18,17 @@ REF = "/root/reference/RayTracing.Test"
 def copy_reference_fixtures():
     shutil.copyfile(os.path.join(REF, "PpmOutputExample.txt"), os.path.join(HERE, "PpmOutputExample.txt"))
     print("wrote PpmOutputExample.txt")
+
+
+def make_earthmap():
+    import numpy as np
+    from PIL import Image
+    with Image.open("/root/reference/RayTracing.App/earthmap.jpg") as im:
+        rgb = np.asarray(im.convert("RGB"), dtype=np.uint8)
+    Image.fromarray(rgb).save(os.path.join(HERE, "earthmap_rgb8.png"), "PNG", optimize=True)
+    with Image.open(os.path.join(HERE, "earthmap_rgb8.png")) as back:
+        assert np.array_equal(np.asarray(back.convert("RGB")), rgb)
+    print(f"wrote earthmap_rgb8.png {rgb.shape}")
 
 
 def make_oracle_frames():
@@ -44,4 +58,5 @@ def make_oracle_frames():
 
 if __name__ == "__main__":
     copy_reference_fixtures()
+    make_earthmap()  # before the frames: C3 is rendered with it
     make_oracle_frames()

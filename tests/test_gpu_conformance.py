@@ -8,7 +8,8 @@ import pytest
 
 import oracle
 from ray_tracing_fsharp_b200 import abi, native, sample_images
-from helpers import camera_sample_rays, f32, random_unit_vectors, scene_pair, small_random_spheres, unit
+from helpers import camera_sample_rays, f32, fp32_safe_closest_hit, random_unit_vectors, scene_pair, small_random_spheres, unit
+from ray_tracing_fsharp_b200.domain import marshal
 
 pytestmark = pytest.mark.gpu
 
@@ -206,52 +207,39 @@ def test_camera_rays(config):
 
 
 # ---- Scene.hitObject -----------------------------------------------------------------------------------------
-def _closest_margin(osc, o, d, prim, t):
-    """Relative gap between the winning t and the runner-up over all objects (brute force, oracle)."""
-    gaps = np.full(len(o), np.inf)
-    for i in range(len(o)):
-        ts = osc.all_hits(o[i], d[i])
-        ts = ts[~np.isnan(ts)]
-        if prim[i] >= 0 and len(ts) > 1:
-            ts = np.sort(ts)
-            gaps[i] = (ts[1] - ts[0]) / ts[0]
-    return gaps
-
-
 @pytest.mark.parametrize("traversal", [0, 1])
 @pytest.mark.parametrize("which", ["C2", "C4", "reduced"])
 def test_hit_object_matches_oracle(which, traversal):
+    """Scene.hitObject (Scene.fs:62-91): the closest primitive is IDENTICAL to the oracle's on every ray whose
+    double-precision margin exceeds FP32 rounding (helpers.fp32_safe_closest_hit: nothing grazed in front of the
+    winner, no origin on a surface, winner leading the runner-up by > 1e-4); the filtered share is asserted small."""
     spec = small_random_spheres() if which == "reduced" else sample_images.CONFIGS[which]()
     osc, dsc, cam = scene_pair(spec)
+    hs, _ts, _keep = marshal(spec.objects)
     rng = np.random.default_rng(8)
     n = 40_000
     o1, d1 = camera_sample_rays(spec, cam, rng, n // 2)
-    # secondary-like rays: from points near the ground, random upward-ish directions
+    # secondary-like rays: from points near the ground, random directions
     o2 = f32(np.stack([rng.uniform(-8, 8, n // 2), rng.uniform(0.45, 2.5, n // 2), rng.uniform(-8, 8, n // 2)], 1))
     d2 = random_unit_vectors(rng, n // 2)
     o, d = np.concatenate([o1, o2]), np.concatenate([d1, d2])
     wp, wt, ws, counters = osc.hit_object(o, d)
     gp, gt, gs = dsc.hit_object(o, d, traversal=traversal)
+    safe = fp32_safe_closest_hit(hs, o, d, wp, wt)
+    filtered = 1.0 - safe.mean()
+    print(f"hit_object {which} traversal={traversal}: {int((~safe).sum())} of {n} rays filtered as not FP32-safe ({filtered:.2%})")
+    assert filtered < 0.12, filtered
     same = wp == gp
+    assert np.array_equal(wp[safe], gp[safe]), f"{int((~same & safe).sum())} FP32-safe rays disagree with the oracle"
+    # unfiltered: decisions may differ only where the margin is tiny
     assert same.mean() > 0.999, same.mean()
-    # every disagreement must be a near-tie or a grazing hit: check the brute-force margin of a sample of them
-    bad = np.nonzero(~same)[0]
-    if len(bad):
-        chk = bad[:50]
-        for i in chk:
-            ts = osc.all_hits(o[i], d[i])
-            ts = np.sort(ts[~np.isnan(ts)])
-            near_tie = len(ts) > 1 and (ts[1] - ts[0]) / ts[0] < 1e-3
-            grazing = True  # a hit / miss flip on a silhouette: cannot be told apart from the t list alone
-            assert near_tie or grazing
-    hit = same & (wp >= 0)
+    hit = safe & (wp >= 0)
     assert hit.sum() > 0.5 * n
     rel = np.abs(gt[hit] - wt[hit]) / wt[hit]
-    # t within 1e-5 relative for all but grazing hits (where FP32 moves the root along the ray)
-    assert np.quantile(rel, 0.999) <= REL, np.quantile(rel, 0.999)
+    assert rel.max() <= REL, rel.max()  # t within 1e-5 relative on every FP32-safe ray
     assert np.median(rel) < 1e-6
     err = np.abs(gs[hit] - ws[hit]).max(1) / (1.0 + np.abs(ws[hit]).max(1))
-    assert np.quantile(err, 0.999) <= REL
+    assert err.max() <= REL
 
 
 def test_negative_radius_bounded_sphere_is_never_hit():

@@ -372,6 +372,37 @@ def test_large_sample_counts_keep_every_sample():
     assert np.abs(sums[..., :3] - ref_stats[..., :3]).max() <= 0.002 * 255 * 2999  # a few paths of 2999 may differ (FP32)
 
 
+@pytest.mark.parametrize("config,max_w,max_h", [("C2", 90, 60), ("C3", 120, 67), ("C4", 80, 45), ("C5", 44, 25)])
+def test_4096_spp_with_the_reference_early_out_against_the_oracle_render(config, max_w, max_h):
+    """BASELINE's level-2 bar for configs[1..4] with the reference's rule ON (renderPixel's early-out, Scene.fs:157-194),
+    on crops (reduced half-extents, same camera and scene) sized so that the oracle finishes in well under a minute:
+    C2 181x121, C3 241x135 (the earth-map texture path), C4 161x91 (planes + glass, depth 100), C5 89x51 (100 000
+    spheres, BVH read from L2).  Oracle: the reference's xorshift128 stream; GPU: Philox — independent streams.
+    Per channel, MAD of the pre-gamma means < 3 sigma-bar (sigma-bar from two GPU seeds); the GPU differs from the oracle
+    no more than from itself under another seed; the share of early-out pixels agrees; P3 bytes are diffed."""
+    spec = _small(config, max_w, max_h, 4096)
+    osc, dsc, cam = scene_pair(spec)
+    ref, ref_stats, counters, _ = osc.render(cam, max_w, max_h, seed=4321, rng_mode=0, adaptive=True)
+    a, sa, _ = dsc.render(cam, max_w, max_h, seed=11, adaptive=True, want_sums=True)
+    b, sb, _ = dsc.render(cam, max_w, max_h, seed=12, adaptive=True, want_sums=True)
+    assert set(np.unique(sa[..., 3]).tolist()) <= {11, 4096} and set(np.unique(ref_stats[..., 3]).tolist()) <= {11, 4096}
+    mean_a, mean_b, mean_o = sa[..., :3] / sa[..., 3:4], sb[..., :3] / sb[..., 3:4], ref_stats[..., :3] / ref_stats[..., 3:4]
+    sigma_bar = np.sqrt(((mean_a - mean_b) ** 2).mean(axis=(0, 1)))
+    mad = np.abs(mean_a - mean_o).mean(axis=(0, 1))
+    mad_gpu = np.abs(mean_a - mean_b).mean(axis=(0, 1))
+    frac_o, frac_g = (ref_stats[..., 3] == 11).mean(), (sa[..., 3] == 11).mean()
+    ppm_g = np.array(ImageOutput.write_ppm(True, a).split()[4:], dtype=np.int32)
+    ppm_o = np.array(oracle.ppm_format(ref, True).split()[4:], dtype=np.int32)
+    diff = np.abs(ppm_g - ppm_o)
+    print(f"{config} {2 * max_w + 1}x{2 * max_h + 1} @4096 spp adaptive: MAD {np.round(mad, 3)} MAD(gpu,gpu') {np.round(mad_gpu, 3)} sigma-bar "
+          f"{np.round(sigma_bar, 3)} early-out oracle {frac_o:.4f} gpu {frac_g:.4f} P3 |diff| <=1: {np.mean(diff <= 1):.3f} mean {diff.mean():.3f}")
+    assert (mad < 3.0 * sigma_bar + 0.25).all(), (mad, sigma_bar)
+    assert (mad < 1.5 * mad_gpu + 0.25).all(), (mad, mad_gpu)
+    assert abs(frac_o - frac_g) < 0.03, (frac_o, frac_g)
+    assert diff.size == 3 * (2 * max_w + 1) * (2 * max_h + 1)
+    assert np.mean(diff <= 3) > 0.8 and np.mean(diff) < 3.0, (np.mean(diff <= 3), np.mean(diff))
+
+
 def test_c1_full_size_4096_spp_against_the_oracle_render():
     """BASELINE's level-2 bar on configs[0] at its real size (401x225), 4096 spp, adaptive early-out on both sides as
     the reference renders: the oracle with the reference's xorshift128 generator, the GPU with Philox — independent

@@ -40,7 +40,7 @@ def test_ctypes_mirror_matches_header_layout():
 int main(void) {
   printf("%zu %zu %zu %zu %zu\n", sizeof(RtTexture), sizeof(RtHittable), sizeof(RtCamera), sizeof(RtRenderOpts), sizeof(RtStats));
   printf("%zu %zu %zu %zu\n", offsetof(RtTexture, rgb8), offsetof(RtTexture, map_radius), offsetof(RtHittable, texture), offsetof(RtCamera, samples_per_pixel));
-  printf("%zu %zu\n", offsetof(RtStats, kernel_ms), offsetof(RtStats, launches));
+  printf("%zu %zu %zu %zu\n", offsetof(RtStats, kernel_ms), offsetof(RtStats, launches), offsetof(RtStats, main_ms), offsetof(RtStats, degenerate_paths));
   return 0; }
 '''
     with tempfile.TemporaryDirectory() as td:
@@ -52,7 +52,7 @@ int main(void) {
     got = [int(x) for x in out]
     want = [C.sizeof(abi.RtTexture), C.sizeof(abi.RtHittable), C.sizeof(abi.RtCamera), C.sizeof(abi.RtRenderOpts), C.sizeof(abi.RtStats),
             abi.RtTexture.rgb8.offset, abi.RtTexture.map_radius.offset, abi.RtHittable.texture.offset, abi.RtCamera.samples_per_pixel.offset,
-            abi.RtStats.kernel_ms.offset, abi.RtStats.launches.offset]
+            abi.RtStats.kernel_ms.offset, abi.RtStats.launches.offset, abi.RtStats.main_ms.offset, abi.RtStats.degenerate_paths.offset]
     assert got == want
 
 

@@ -165,3 +165,34 @@ def test_trace_ray_terminal_colours():
     assert col[0].tolist() == [0, 0, 0] and rays[0] == 1
     col, rays = _scene([Hittable.UnboundedSphere(Sphere.make(lam, (0, 0, 0), 50.0))]).trace_samples(cam, 5, 5, 1, rows, rows, [0])
     assert col[0].tolist() == [205, 105, 180] and rays[0] == 4     # maxCount + 1 interactions
+
+
+def test_earth_map_row_flip_and_lookup_on_the_real_bitmap():
+    """The `earth` path on the real decoded picture (SampleImages.fs:962-968): ParameterisedTexture.ofImage stores row
+    img.Height - y - 1 of the bitmap as img.[y] (Texture.fs:30-48), and colourAt (Texture.fs:63-67) reads
+    img.[int (v (H - 1))].[int ((1 - u) (W - 1))] with (u, v) = Sphere.planeMapInverse (Sphere.fs:55-61).  Written here
+    from those lines in numpy, independently of the oracle, and compared with the oracle's lookup on the committed
+    decode of earthmap.jpg — so that the flip has met a real bitmap: the picture is far from symmetric top to bottom."""
+    import oracle
+    from ray_tracing_fsharp_b200 import sample_images
+    from ray_tracing_fsharp_b200.domain import ParameterisedTexture, marshal
+    bitmap, source = sample_images.load_earthmap()
+    assert source.startswith("earthmap.jpg"), source  # the fixture is committed; the synthetic stand-in must not be what runs
+    assert bitmap.shape == (512, 1024, 3)
+    assert np.abs(bitmap[:40].astype(int).mean() - bitmap[-40:].astype(int).mean()) > 1.0  # top and bottom differ
+    img = ParameterisedTexture.of_image(bitmap).img
+    assert np.array_equal(img[0], bitmap[511]) and np.array_equal(img[511], bitmap[0]) and np.array_equal(img[100, 7], bitmap[411, 7])
+    spec = sample_images.earth()
+    hs, ts, _keep = marshal(spec.objects)
+    osc = oracle.Scene(hs, ts)
+    rng = np.random.default_rng(21)
+    p = rng.normal(size=(20000, 3))
+    p /= np.sqrt((p * p).sum(1, keepdims=True))
+    got = osc.texture(np.zeros(len(p), np.int32), p)
+    theta = np.arccos(np.clip(-p[:, 1], -1.0, 1.0))
+    phi = np.arctan2(-p[:, 2], p[:, 0]) + np.pi
+    u, v = phi / (2 * np.pi), theta / np.pi
+    x = ((1.0 - u) * 1023).astype(int)
+    y = (v * 511).astype(int)
+    want = bitmap[511 - y, x]  # img.[y] is bitmap row H - 1 - y
+    assert (got == want).all(1).mean() > 0.9999
