@@ -210,7 +210,9 @@ class Runner:
         if self.world > 1:
             dist.init_process_group("nccl", device_id=self.dev)
             self.ctl = dist.new_group(backend="gloo")  # host-side barrier for the phases where rank 0 drives every GPU itself
-        self.stream = torch.cuda.current_stream(self.dev)
+        # a stream of our own, made current: the legacy default stream's handle is NULL, which the library reads as "use your own"
+        self.stream = torch.cuda.Stream(self.dev)
+        torch.cuda.set_stream(self.stream)
         self.comm = comm_from_torch_distributed(self.local_rank, self.stream.cuda_stream)
         self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)  # > 126 MB L2
         self.adaptive = not args.no_adaptive

@@ -13,7 +13,9 @@ Reference types mirrored:
   InfinitePlaneStyle, InfinitePlane RayTracing/InfinitePlane.fs:3-13, :101-119
   Hittable                          RayTracing/Hittable.fs:3-6
 """
+import ctypes
 import math
+import struct
 from dataclasses import dataclass, field
 from typing import Any, List, Optional, Sequence, Tuple
 
@@ -322,85 +324,89 @@ class _TextureTable:
         return len(self.entries) - 1
 
 
-def _set_texture(h: abi.RtHittable, tex, table: _TextureTable):
+_HITTABLE = struct.Struct("<ii3d3d5di3Bx")  # RtHittable, include/rtfs_b200.h (layout checked in tests/test_host_cpu.py)
+assert _HITTABLE.size == ctypes.sizeof(abi.RtHittable)
+_TEXTURE_OFFSET = abi.RtHittable.texture.offset
+
+
+def _texture_of(tex):
+    """(constant colour, Texture.Parameterised or None) of a style's texture field."""
     if isinstance(tex, Texture.Colour):
-        h.texture = -1
-        h.colour[:] = tex.pixel.as_tuple()
-    elif isinstance(tex, Pixel):
-        h.texture = -1
-        h.colour[:] = tex.as_tuple()
-    elif isinstance(tex, Texture.Parameterised):
-        h.texture = table.add_param(tex.interpret, tex.texture)
+        return tex.pixel.as_tuple(), None
+    if isinstance(tex, Pixel):
+        return tex.as_tuple(), None
+    if isinstance(tex, Texture.Parameterised):
+        return (0, 0, 0), tex
+    raise NotImplementedError("Texture.Arbitrary is a host closure and cannot be evaluated on the device (RT_ERR_UNSUPPORTED)")
+
+
+def _pack(obj):
+    """The RtHittable record of one Hittable (texture index -1) and its Texture.Parameterised, if it has one.  The record
+    is kept on the (immutable) object: Scene.make on a scene built once costs one memcpy per object afterwards, which is
+    what the F# shim's marshalling loop costs."""
+    albedo = fuzz = ior = prob = 0.0
+    colour, ptex = (0, 0, 0), None
+    n = (0.0, 0.0, 0.0)
+    if isinstance(obj, (Hittable.Sphere, Hittable.UnboundedSphere)):
+        s = obj.sphere
+        shape = abi.RT_SHAPE_SPHERE if isinstance(obj, Hittable.Sphere) else abi.RT_SHAPE_UNBOUNDED_SPHERE
+        p, radius, st = s.Centre, s.Radius, s.Style
+        if isinstance(st, SphereStyle.LightSource):
+            style = abi.RT_STYLE_LIGHT_SOURCE
+            colour, ptex = _texture_of(st.texture)
+        elif isinstance(st, SphereStyle.LightSourceCap):
+            style, colour = abi.RT_STYLE_LIGHT_SOURCE_CAP, st.colour.as_tuple()
+        elif isinstance(st, SphereStyle.PureReflection):
+            style, albedo = abi.RT_STYLE_PURE_REFLECTION, st.albedo
+            colour, ptex = _texture_of(st.texture)
+        elif isinstance(st, SphereStyle.FuzzedReflection):
+            style, albedo, fuzz = abi.RT_STYLE_FUZZED_REFLECTION, st.albedo, st.fuzz
+            colour, ptex = _texture_of(st.texture)
+        elif isinstance(st, SphereStyle.LambertReflection):
+            style, albedo = abi.RT_STYLE_LAMBERT_REFLECTION, st.albedo
+            colour, ptex = _texture_of(st.texture)
+        elif isinstance(st, SphereStyle.Dielectric):
+            style, albedo, ior, prob = abi.RT_STYLE_DIELECTRIC, st.albedo, st.boundaryRefractance, st.refraction
+            colour, ptex = _texture_of(st.texture)
+        elif isinstance(st, SphereStyle.Glass):
+            style, albedo, ior = abi.RT_STYLE_GLASS, st.albedo, st.ior
+            colour, ptex = _texture_of(st.texture)
+        else:
+            raise TypeError(f"unknown SphereStyle {st!r}")
+    elif isinstance(obj, Hittable.InfinitePlane):
+        pl = obj.plane
+        shape, p, n, radius, st = abi.RT_SHAPE_INFINITE_PLANE, pl.Point, pl.Normal, 0.0, pl.Style
+        if isinstance(st, InfinitePlaneStyle.LightSource):
+            style = abi.RT_STYLE_LIGHT_SOURCE
+            colour, ptex = _texture_of(st.texture)
+        elif isinstance(st, InfinitePlaneStyle.PureReflection):
+            style, albedo, colour = abi.RT_STYLE_PURE_REFLECTION, st.albedo, st.colour.as_tuple()
+        elif isinstance(st, InfinitePlaneStyle.LambertReflection):
+            style, albedo, colour = abi.RT_STYLE_LAMBERT_REFLECTION, st.albedo, st.colour.as_tuple()
+        elif isinstance(st, InfinitePlaneStyle.FuzzedReflection):
+            style, albedo, fuzz, colour = abi.RT_STYLE_FUZZED_REFLECTION, st.albedo, st.fuzz, st.colour.as_tuple()
+        else:
+            raise TypeError(f"unknown InfinitePlaneStyle {st!r}")
     else:
-        raise NotImplementedError(
-            "Texture.Arbitrary is a host closure and cannot be evaluated on the device (RT_ERR_UNSUPPORTED)")
+        raise TypeError(f"not a Hittable: {obj!r}")
+    rec = (_HITTABLE.pack(shape, style, p[0], p[1], p[2], n[0], n[1], n[2], radius, albedo, fuzz, ior, prob, -1, colour[0], colour[1], colour[2]), ptex)
+    object.__setattr__(obj, "_abi", rec)  # frozen dataclass: plain attribute, not a field
+    return rec
 
 
 def marshal(objects: Sequence[Any]):
-    """Hittable array -> (list[RtHittable], list[RtTexture], keepalive)."""
+    """Hittable array -> (RtHittable array, list[RtTexture], keepalive): what the F# shim's marshalling loop produces.
+    The first result is a ctypes array (indexable and iterable like a list of RtHittable) over one contiguous buffer."""
     table = _TextureTable()
-    out = []
-    for obj in objects:
-        h = abi.RtHittable()
-        h.texture = -1
-        if isinstance(obj, (Hittable.Sphere, Hittable.UnboundedSphere)):
-            s = obj.sphere
-            h.shape = abi.RT_SHAPE_SPHERE if isinstance(obj, Hittable.Sphere) else abi.RT_SHAPE_UNBOUNDED_SPHERE
-            h.p[:] = s.Centre
-            h.radius = s.Radius
-            st = s.Style
-            if isinstance(st, SphereStyle.LightSource):
-                h.style = abi.RT_STYLE_LIGHT_SOURCE
-                _set_texture(h, st.texture, table)
-            elif isinstance(st, SphereStyle.LightSourceCap):
-                h.style = abi.RT_STYLE_LIGHT_SOURCE_CAP
-                h.colour[:] = st.colour.as_tuple()
-            elif isinstance(st, SphereStyle.PureReflection):
-                h.style = abi.RT_STYLE_PURE_REFLECTION
-                h.albedo = st.albedo
-                _set_texture(h, st.texture, table)
-            elif isinstance(st, SphereStyle.FuzzedReflection):
-                h.style = abi.RT_STYLE_FUZZED_REFLECTION
-                h.albedo, h.fuzz = st.albedo, st.fuzz
-                _set_texture(h, st.texture, table)
-            elif isinstance(st, SphereStyle.LambertReflection):
-                h.style = abi.RT_STYLE_LAMBERT_REFLECTION
-                h.albedo = st.albedo
-                _set_texture(h, st.texture, table)
-            elif isinstance(st, SphereStyle.Dielectric):
-                h.style = abi.RT_STYLE_DIELECTRIC
-                h.albedo, h.ior, h.prob = st.albedo, st.boundaryRefractance, st.refraction
-                _set_texture(h, st.texture, table)
-            elif isinstance(st, SphereStyle.Glass):
-                h.style = abi.RT_STYLE_GLASS
-                h.albedo, h.ior = st.albedo, st.ior
-                _set_texture(h, st.texture, table)
-            else:
-                raise TypeError(f"unknown SphereStyle {st!r}")
-        elif isinstance(obj, Hittable.InfinitePlane):
-            p = obj.plane
-            h.shape = abi.RT_SHAPE_INFINITE_PLANE
-            h.p[:] = p.Point
-            h.n[:] = p.Normal
-            st = p.Style
-            if isinstance(st, InfinitePlaneStyle.LightSource):
-                h.style = abi.RT_STYLE_LIGHT_SOURCE
-                _set_texture(h, st.texture, table)
-            elif isinstance(st, InfinitePlaneStyle.PureReflection):
-                h.style = abi.RT_STYLE_PURE_REFLECTION
-                h.albedo = st.albedo
-                h.colour[:] = st.colour.as_tuple()
-            elif isinstance(st, InfinitePlaneStyle.LambertReflection):
-                h.style = abi.RT_STYLE_LAMBERT_REFLECTION
-                h.albedo = st.albedo
-                h.colour[:] = st.colour.as_tuple()
-            elif isinstance(st, InfinitePlaneStyle.FuzzedReflection):
-                h.style = abi.RT_STYLE_FUZZED_REFLECTION
-                h.albedo, h.fuzz = st.albedo, st.fuzz
-                h.colour[:] = st.colour.as_tuple()
-            else:
-                raise TypeError(f"unknown InfinitePlaneStyle {st!r}")
-        else:
-            raise TypeError(f"not a Hittable: {obj!r}")
-        out.append(h)
+    recs, textured = [], []
+    for i, obj in enumerate(objects):
+        rec = getattr(obj, "_abi", None) or _pack(obj)
+        recs.append(rec[0])
+        if rec[1] is not None:
+            textured.append((i, rec[1]))
+    buf = bytearray(b"".join(recs))
+    for i, tex in textured:
+        struct.pack_into("<i", buf, i * _HITTABLE.size + _TEXTURE_OFFSET, table.add_param(tex.interpret, tex.texture))
+    n = len(recs)
+    out = (abi.RtHittable * n).from_buffer(buf) if n else (abi.RtHittable * 0)()
     return out, table.entries, table.keep

@@ -140,6 +140,13 @@ def _frame_buffer(shape):
     return buf
 
 
+def _as_array(ctype, items):
+    """A ctypes array of `items` for the ABI: marshal()'s array is passed through as it is (no per-element copy)."""
+    if isinstance(items, C.Array) and items._type_ is ctype and len(items) > 0:
+        return items
+    return (ctype * max(1, len(items)))(*items)
+
+
 def device_count():
     return int(lib().rt_device_count())
 
@@ -149,8 +156,8 @@ class SceneHandle:
 
     def __init__(self, hittables, textures=(), device=0, keepalive=None):
         self.n_objects = len(hittables)
-        self._h = (RtHittable * max(1, len(hittables)))(*hittables)
-        self._t = (RtTexture * max(1, len(textures)))(*textures)
+        self._h = _as_array(RtHittable, hittables)
+        self._t = _as_array(RtTexture, textures)
         self._keep = keepalive
         self.device = device
         out = C.c_void_p()
@@ -240,8 +247,8 @@ class MultiHandle:
     """Owner of an RtMulti* (rt_multi_create / rt_multi_destroy): one frame split over several GPUs of this process."""
 
     def __init__(self, hittables, textures=(), devices=(0,), keepalive=None):
-        self._h = (RtHittable * max(1, len(hittables)))(*hittables)
-        self._t = (RtTexture * max(1, len(textures)))(*textures)
+        self._h = _as_array(RtHittable, hittables)
+        self._t = _as_array(RtTexture, textures)
         self._keep = keepalive
         self.devices = list(devices)
         dv = (C.c_int32 * len(self.devices))(*self.devices)
