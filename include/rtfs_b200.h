@@ -129,6 +129,9 @@ typedef struct RtRenderOpts {
 /* RtRenderOpts.flags */
 #define RT_FLAG_COUNTERS 1 /* also count the device traversal's box / primitive tests (slower kernel variant) */
 #define RT_FLAG_NO_SMEM 2  /* read the BVH from global memory even when it would fit in shared memory      */
+#define RT_FLAG_WIDE_BVH 4 /* walk the 8-wide compressed tree (global memory) whatever the scene's size; the default
+                              for scenes too large for shared memory                                           */
+#define RT_FLAG_BVH2 8     /* walk the binary tree even where the wide one is the default (A/B comparisons)   */
 
 typedef struct RtStats {
     uint64_t paths;     /* traceOnce calls (Scene.fs:118)                                        */
@@ -189,6 +192,12 @@ void rt_scene_destroy(RtScene *scene);
 int rt_scene_bvh_node_count(const RtScene *scene, int32_t which /* RtBvhKind */);
 int rt_scene_bvh_nodes(const RtScene *scene, int32_t which, double *bounds, int32_t *right,
                        int32_t *prim);
+/* The third tree: the 8-wide compressed BVH the render kernels walk for scenes read from global memory (quantised
+ * child boxes, 80-byte nodes; replaces BoundingBoxTree.fs:9-43 / Scene.fs:30-60 for those scenes).  Builds it on the
+ * host if need be and verifies it: every bounded sphere in exactly one leaf slot, every decoded box containing what
+ * lies below it (RT_ERR_DEGENERATE otherwise).  Outputs are optional. */
+int rt_scene_wide_bvh_check(RtScene *scene, int32_t *n_nodes, int32_t *depth, int32_t *n_spheres,
+                            double *mean_children);
 /* bytes of scene data resident on the device (nodes + primitives + materials + textures) */
 size_t rt_scene_device_bytes(const RtScene *scene);
 /* bytes of BVH + spheres + materials that every persistent block stages in shared memory; 0 when the scene
@@ -307,8 +316,9 @@ int rt_test_plane_hit(int32_t device, int32_t n, const double *origin, const dou
 int rt_test_aabb_hit(int32_t device, int32_t n, const double *origin, const double *dir,
                      const double *box_min, const double *box_max, uint8_t *hit_out);
 /* Scene.hitObject (Scene.fs:62-91).  prim_out = index into the caller's Hittable array or -1;
- * traversal: 0 = the render kernels' ordered/culled traversal of the SAH tree,
- *            1 = exhaustive left-then-right DFS of the reference-topology tree (F12). */
+ * traversal: 0 = the render kernels' ordered/culled traversal of the binary SAH tree,
+ *            1 = exhaustive left-then-right DFS of the reference-topology tree (F12),
+ *            2 = the render kernels' traversal of the 8-wide compressed tree (big scenes, RT_FLAG_WIDE_BVH). */
 int rt_test_hit_object(RtScene *scene, int32_t traversal, int32_t n, const double *origin,
                        const double *dir, int32_t *prim_out, double *t_out, double *strike_out);
 /* Hittable.Reflection (Hittable.fs:8-12 -> Sphere.fs:150-300 / InfinitePlane.fs:43-99) with

@@ -39,6 +39,8 @@ RT_MODE_WAVEFRONT = 1
 
 RT_FLAG_COUNTERS = 1
 RT_FLAG_NO_SMEM = 2
+RT_FLAG_WIDE_BVH = 4
+RT_FLAG_BVH2 = 8
 
 RT_COMM_ID_BYTES = 128
 

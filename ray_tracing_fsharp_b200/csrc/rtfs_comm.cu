@@ -215,6 +215,7 @@ int rt_comm_render(RtComm *c, RtScene *scene, const RtCamera *camera, int32_t ma
     int rc = check_frame_args(scene, camera, max_w, max_h, opts);
     if (rc != RT_OK) return rc;
     if (opts->mode != RT_MODE_MEGAKERNEL) return fail(RT_ERR_UNSUPPORTED, "rt_comm_render: only RT_MODE_MEGAKERNEL is split over ranks");
+    if ((rc = prepare_frame(scene, opts)) != RT_OK) return rc;
     auto *ds = static_cast<DeviceScene *>(scene->dev);
     if (ds->device != c->device) return fail(RT_ERR_INVALID_ARGUMENT, "rt_comm_render: the scene lives on another device than the communicator");
     RT_CUDA(cudaSetDevice(c->device));

@@ -96,7 +96,10 @@ __global__ void k_hit_object(SceneGlobal g, const DRefNode *ref_nodes, int n_ref
         sc.g = g;
         sc.s_nodes = sc.s_spheres = sc.s_mats = 0;
         TraversalCounters cn{0, 0};
-        h = closest_hit<false, false>(sc, ld3(o, i), ld3(d, i), kNoPrim, cn, 1u << (threadIdx.x & 31));
+        if (traversal == 2)
+            h = closest_hit<false, false, true>(sc, ld3(o, i), ld3(d, i), kNoPrim, cn, 1u << (threadIdx.x & 31));
+        else
+            h = closest_hit<false, false>(sc, ld3(o, i), ld3(d, i), kNoPrim, cn, 1u << (threadIdx.x & 31));
     }
     if (h.prim == kNoPrim) {
         prim_out[i] = -1;
@@ -297,8 +300,9 @@ int rt_test_hit_object(RtScene *scene, int32_t traversal, int32_t n, const doubl
     DeviceScene *ds;
     RT_TRY(scene_device(scene, &ds));
     if (n < 0 || !origin || !dir || !prim_out || !t_out) return fail(RT_ERR_INVALID_ARGUMENT, "rt_test_hit_object: bad argument");
-    if (traversal != 0 && traversal != 1) return fail(RT_ERR_INVALID_ARGUMENT, "rt_test_hit_object: traversal must be 0 or 1");
+    if (traversal < 0 || traversal > 2) return fail(RT_ERR_INVALID_ARGUMENT, "rt_test_hit_object: traversal must be 0, 1 or 2");
     if (traversal == 1) RT_TRY(device_scene_ensure_reference(scene));
+    if (traversal == 2) RT_TRY(device_scene_ensure_wide(scene));
     DevBuf<float> o, d, t, s;
     DevBuf<int32_t> p;
     RT_TRY(o.put(to_f32(origin, 3 * size_t(n))));

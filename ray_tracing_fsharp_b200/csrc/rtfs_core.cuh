@@ -343,6 +343,11 @@ struct SceneGlobal {
     const DUnbounded *unb;
     const DTexture *tex;
     int32_t n_nodes, n_bounded, n_unbounded, n_tex;
+    // the 8-wide compressed tree (null until built: big scenes at creation, others on first use)
+    const uint4 *wide_nodes;      // 5 per node
+    const float4 *wide_spheres;   // the spheres in the wide tree's order
+    const int32_t *wide_to_dev;   // wide sphere index -> device primitive id
+    const int32_t *dev_to_wide;   // and back
 };
 
 #ifdef __CUDACC__
@@ -354,6 +359,14 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     return v;
 }
 #endif
+
+RTFS_HD float4 ldg_sphere(const float4 *p) {
+#ifdef __CUDA_ARCH__
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
 
 template <bool SMEM>
 struct SceneAccess {
@@ -456,6 +469,9 @@ struct LocalStack {
     int a[64];
     RTFS_HD void put(int i, int v) { a[i] = v; }
     RTFS_HD int get(int i) const { return a[i]; }
+    // two-word entries (the wide walk's node groups)
+    RTFS_HD void put2(int i, uint2 v) { a[2 * i] = int(v.x); a[2 * i + 1] = int(v.y); }
+    RTFS_HD uint2 get2(int i) const { return make_uint2(uint32_t(a[2 * i]), uint32_t(a[2 * i + 1])); }
 };
 #ifdef __CUDACC__
 struct SharedStack {
@@ -464,6 +480,18 @@ struct SharedStack {
     __device__ __forceinline__ int get(int i) const {
         int v;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base + uint32_t(i) * stride));
+        return v;
+    }
+    __device__ __forceinline__ void put2(int i, uint2 v) {
+        const uint32_t a = base + uint32_t(2 * i) * stride;
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v.x));
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(a + stride), "r"(v.y));
+    }
+    __device__ __forceinline__ uint2 get2(int i) const {
+        const uint32_t a = base + uint32_t(2 * i) * stride;
+        uint2 v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v.x) : "r"(a));
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v.y) : "r"(a + stride));
         return v;
     }
 };
@@ -510,10 +538,117 @@ RTFS_HD bool bvh_visit(const SceneAccess<SMEM> &sc, const RaySlabs &rs, float3 o
     node = stack.get(--sp);
     return false;
 }
+// ---- the 8-wide compressed tree (scenes read from global memory) -------------------------------------------------
+// After Ylitie, Karras, Laine (HPG 2017).  A visit loads one 80-byte node (five 128-bit read-only loads: three 32-byte
+// sectors instead of the two per BVH2 visit, for a third as many visits), tests its eight quantised child boxes against
+// the ray and the best hit so far, and turns the outcome into one 32-bit mask: bits 24..31 = internal children that
+// were hit, at position 24 + (slot XOR octant of the ray), so that the highest set bit is always the child to enter
+// next (front to back without computing or sorting distances); bits 0..23 = spheres of the node's leaf children.  The
+// walk holds a "node group" {child_base, hit bits | imask}: popping a child is a find-highest-bit and a popcount; a
+// group with children left over goes on the stack as ONE two-word entry.
+//
+// A quantised plane byte b becomes the float 1 + b 2^-15 with one PRMT (b dropped into the mantissa of 1.0f), so a
+// plane distance is one FFMA, t = f S + C, with per node and axis S = 2^(e+15) / d and C = (p - o) / d - S: no integer to
+// float conversions (a quarter-rate pipe).  The test is conservative: boxes are quantised outwards, t_far is padded.
+// Refs here: a sphere is named ~k with k its index in the WIDE sphere order (wide_to_dev maps it to the device id).
+#ifdef __CUDACC__
+RTFS_HD float wide_plane(uint32_t q4, int j) { // byte j of q4 -> 1 + b 2^-15
+    return __uint_as_float(__byte_perm(q4, 0x3F800000u, 0x7640u | (uint32_t(j) << 4)));
+}
+RTFS_HD uint32_t sign_extend_s8x4(uint32_t x) { return __byte_perm(x, 0u, 0xba98u); }
+RTFS_HD uint4 ldg128(const uint4 *p) { return __ldg(p); }
+#else
+RTFS_HD float wide_plane(uint32_t q4, int j) { return 1.0f + float((q4 >> (8 * j)) & 255u) * 3.0517578125e-05f; }
+RTFS_HD uint32_t sign_extend_s8x4(uint32_t x) {
+    uint32_t r = 0;
+    for (int j = 0; j < 4; ++j)
+        if ((x >> (8 * j + 7)) & 1u) r |= 0xffu << (8 * j);
+    return r;
+}
+RTFS_HD uint4 ldg128(const uint4 *p) { return *p; }
+RTFS_HD int __clz(uint32_t x) { return x ? __builtin_clz(x) : 32; }
+RTFS_HD int __popc(uint32_t x) { return __builtin_popcount(x); }
+#endif
+template <bool COUNT, class Stack>
+RTFS_HD void wide_closest(const SceneGlobal &g, float3 o, float3 d, int last_ref, float &best_t, int &best_ref, TraversalCounters &cn, Stack &stack) {
+    best_t = kNoHitT;
+    best_ref = kNoRef;
+    if (g.n_bounded <= 0) return;
+    const RaySlabs rs = make_slabs(o, d);
+    const bool nx = rs.inv.x < 0.0f, ny = rs.inv.y < 0.0f, nz = rs.inv.z < 0.0f;
+    const uint32_t octinv = (nx ? 0u : 4u) | (ny ? 0u : 2u) | (nz ? 0u : 1u);
+    const uint32_t octinv4 = octinv * 0x01010101u;
+    uint2 ngroup = make_uint2(0u, 0x80000000u); // the root: "child 0 of a group at base 0"
+    int sp = 0;
+    for (;;) {
+        // ---- enter the nearest child of the current group ----
+        const uint32_t bit = 31u - uint32_t(__clz(ngroup.y));
+        const uint32_t imask_bits = ngroup.y;
+        ngroup.y &= ~(1u << bit);
+        if (ngroup.y > 0x00FFFFFFu) stack.put2(sp++, ngroup);
+        const uint32_t slot = (bit - 24u) ^ octinv;
+        const uint32_t node = ngroup.x + uint32_t(__popc(imask_bits & ~(0xFFFFFFFFu << slot)));
+        const uint4 *np = g.wide_nodes + 5 * size_t(node);
+        const uint4 n0 = ldg128(np), n1 = ldg128(np + 1), n2 = ldg128(np + 2), n3 = ldg128(np + 3), n4 = ldg128(np + 4);
+        if (COUNT) cn.box_tests += 8;
+        // per node and axis: t(b) = f(b) S + C
+        const float sx = __uint_as_float((n0.w & 0xffu) << 23) * rs.inv.x;
+        const float sy = __uint_as_float((n0.w & 0xff00u) << 15) * rs.inv.y;
+        const float sz = __uint_as_float((n0.w & 0xff0000u) << 7) * rs.inv.z;
+        const float bx = fmaf(__uint_as_float(n0.x), rs.inv.x, rs.noi.x), by = fmaf(__uint_as_float(n0.y), rs.inv.y, rs.noi.y),
+                    bz = fmaf(__uint_as_float(n0.z), rs.inv.z, rs.noi.z);
+        const float cx = bx - sx, cy = by - sy, cz = bz - sz;
+        // rounding of b (relative to |b|), of C (relative to |b| + |S|) and of noi (rs.pad), as an absolute pad on t_far
+        const float pad = fmaf(2.4e-7f, fmaxf(fmaxf(fabsf(bx) + fabsf(sx), fabsf(by) + fabsf(sy)), fabsf(bz) + fabsf(sz)), rs.pad);
+        uint32_t hits = 0;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const uint32_t meta4 = half ? n1.w : n1.z;
+            const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+            const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
+            const uint32_t bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1F1F1F1Fu;
+            const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+            const uint32_t qlx = half ? n2.y : n2.x, qly = half ? n2.w : n2.z, qlz = half ? n3.y : n3.x;
+            const uint32_t qhx = half ? n3.w : n3.z, qhy = half ? n4.y : n4.x, qhz = half ? n4.w : n4.z;
+            const uint32_t near_x = nx ? qhx : qlx, far_x = nx ? qlx : qhx;
+            const uint32_t near_y = ny ? qhy : qly, far_y = ny ? qly : qhy;
+            const uint32_t near_z = nz ? qhz : qlz, far_z = nz ? qlz : qhz;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float t0x = fmaf(wide_plane(near_x, j), sx, cx), t1x = fmaf(wide_plane(far_x, j), sx, cx);
+                const float t0y = fmaf(wide_plane(near_y, j), sy, cy), t1y = fmaf(wide_plane(far_y, j), sy, cy);
+                const float t0z = fmaf(wide_plane(near_z, j), sz, cz), t1z = fmaf(wide_plane(far_z, j), sz, cz);
+                const float t_near = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.0f));
+                const float t_far = fminf(fminf(t1x, t1y), fminf(t1z, best_t));
+                if (t_near <= fmaf(t_far, 1.0000003576278687f, pad)) hits |= ((child_bits4 >> (8 * j)) & 0xffu) << ((bit_index4 >> (8 * j)) & 0xffu);
+            }
+        }
+        ngroup = make_uint2(n1.x, (hits & 0xFF000000u) | (n0.w >> 24));
+        // ---- the spheres of this node's leaf children that the ray may hit ----
+        uint32_t prims = hits & 0x00FFFFFFu;
+        while (prims) {
+            const uint32_t pb = 31u - uint32_t(__clz(prims));
+            prims &= ~(1u << pb);
+            const int k = int(n1.y + pb);
+            float t;
+            if (COUNT) cn.prim_tests += 1;
+            if (sphere_hit(o, d, ldg_sphere(g.wide_spheres + k), ~k == last_ref, t) && t < best_t) {
+                best_t = t;
+                best_ref = ~k;
+            }
+        }
+        if (ngroup.y <= 0x00FFFFFFu) {
+            if (sp == 0) return;
+            ngroup = stack.get2(--sp);
+        }
+    }
+}
+
 // A path remembers the primitive its ray leaves as the walk names it: the leaf ref of a bounded sphere (< 0), the
 // device id of an unbounded object (>= n_bounded), kNoRef for a camera ray.  From a device primitive id:
-template <bool SMEM>
+template <bool SMEM, bool WIDE = false>
 RTFS_HD int ref_of_prim(const SceneAccess<SMEM> &sc, int prim) {
+    if (WIDE) return prim < 0 ? kNoRef : (prim < sc.g.n_bounded ? ~sc.g.dev_to_wide[prim] : prim);
     return prim < 0 ? kNoRef : (prim < sc.g.n_bounded ? sc.ref_of_sphere(prim) : prim);
 }
 // the bounded part of hitObject: the closest sphere of the tree, if any
@@ -531,7 +666,7 @@ RTFS_HD void bvh_closest(const SceneAccess<SMEM> &sc, float3 o, float3 d, int la
 }
 // the unbounded objects, after the tree (Scene.fs:77-86), and the strike point (:91)
 // (`last_ref` and `best_ref` are refs; an unbounded object's ref is its device id)
-template <bool SMEM, bool COUNT>
+template <bool SMEM, bool COUNT, bool WIDE = false>
 RTFS_HD Hit finish_hit(const SceneAccess<SMEM> &sc, float3 o, float3 d, int last_ref, float best_t, int best_ref, TraversalCounters &cn) {
     const int last = last_ref;
     int best = best_ref;
@@ -554,7 +689,7 @@ RTFS_HD Hit finish_hit(const SceneAccess<SMEM> &sc, float3 o, float3 d, int last
     Hit h;
     h.t = best_t;
     h.ref = best;
-    h.prim = best < 0 ? sc.sphere_of_ref(best) : (best == kNoRef ? kNoPrim : best);
+    h.prim = best < 0 ? (WIDE ? sc.g.wide_to_dev[~best] : sc.sphere_of_ref(best)) : (best == kNoRef ? kNoPrim : best);
     h.strike = fma3(best_t, d, o); // Ray.walkAlong ray bestLength, Scene.fs:91
     return h;
 }
@@ -563,19 +698,22 @@ RTFS_HD Hit finish_hit(const SceneAccess<SMEM> &sc, float3 o, float3 d, int last
 // full width instead of once per straggler group.
 // (Tried and dropped: parking a leaf and testing it after the walk, converged, instead of during it at ~4 active
 // lanes — the lost culling costs 5 % more slab tests and the C2 frame got 3 % slower.)
-template <bool SMEM, bool COUNT, class Stack>
+template <bool SMEM, bool COUNT, class Stack, bool WIDE = false>
 RTFS_HD Hit closest_hit_from(const SceneAccess<SMEM> &sc, float3 o, float3 d, int last_ref, TraversalCounters &cn, unsigned lanes, Stack &stack) {
     float best_t;
     int best_ref;
-    bvh_closest<SMEM, COUNT>(sc, o, d, last_ref, best_t, best_ref, cn, stack);
+    if (WIDE)
+        wide_closest<COUNT>(sc.g, o, d, last_ref, best_t, best_ref, cn, stack);
+    else
+        bvh_closest<SMEM, COUNT>(sc, o, d, last_ref, best_t, best_ref, cn, stack);
     converge(lanes);
-    return finish_hit<SMEM, COUNT>(sc, o, d, last_ref, best_t, best_ref, cn);
+    return finish_hit<SMEM, COUNT, WIDE>(sc, o, d, last_ref, best_t, best_ref, cn);
 }
 // the same with the ray's previous primitive given as a device primitive id (conformance entry points, wavefront)
-template <bool SMEM, bool COUNT>
+template <bool SMEM, bool COUNT, bool WIDE = false>
 RTFS_HD Hit closest_hit(const SceneAccess<SMEM> &sc, float3 o, float3 d, int last, TraversalCounters &cn, unsigned lanes) {
     LocalStack stack;
-    return closest_hit_from<SMEM, COUNT>(sc, o, d, ref_of_prim(sc, last), cn, lanes, stack);
+    return closest_hit_from<SMEM, COUNT, LocalStack, WIDE>(sc, o, d, ref_of_prim<SMEM, WIDE>(sc, last), cn, lanes, stack);
 }
 
 // The reference's own traversal (Scene.fs:30-60, F12): exhaustive left-then-right DFS of the
@@ -878,10 +1016,10 @@ RTFS_HD bool path_after_hit(PathState &p, const SceneAccess<SMEM> &sc, const Hit
     return false;
 }
 // one whole step: hitObject + Reflection; returns true when the path is finished
-template <bool SMEM, bool COUNT, class Stack>
+template <bool SMEM, bool COUNT, class Stack, bool WIDE = false>
 RTFS_HD bool path_step(PathState &p, const SceneAccess<SMEM> &sc, int max_count, uint32_t &result, TraversalCounters &cn, unsigned lanes,
                        Stack &stack) {
-    Hit h = closest_hit_from<SMEM, COUNT>(sc, p.o, p.d, p.last, cn, lanes, stack);
+    Hit h = closest_hit_from<SMEM, COUNT, Stack, WIDE>(sc, p.o, p.d, p.last, cn, lanes, stack);
     return path_after_hit<SMEM>(p, sc, h, max_count, result);
 }
 

@@ -136,6 +136,7 @@ void device_scene_free(RtScene *scene) {
     cudaDeviceSynchronize();
     cudaFree(ds->ref_nodes);
     cudaFree(ds->blob);
+    cudaFree(ds->wide_blob);
     if (ds->ws) workspace_release(ds->ws);
     for (const PooledTexture &t : ds->images) texture_release(t);
     delete ds;
@@ -224,6 +225,50 @@ int device_scene_upload(RtScene *scene) {
     ds->g.n_unbounded = int32_t(L.unbounded.size());
     ds->g.n_tex = int32_t(scene->textures.size());
     ds->max_depth = L.max_depth;
+    if (!L.wide_nodes.empty()) return device_scene_ensure_wide(scene); // built at creation for big scenes
+    return RT_OK;
+}
+
+// uploads the 8-wide compressed tree (building it first if the scene was too small to get one at creation)
+int device_scene_ensure_wide(RtScene *scene) {
+    auto *ds = static_cast<DeviceScene *>(scene->dev);
+    if (!ds || ds->wide_blob || ds->g.n_bounded <= 0) return RT_OK;
+    HostSceneLayout &L = scene->layout;
+    build_wide_layout(L);
+    if (L.wide_depth > 30) return fail(RT_ERR_UNSUPPORTED, "the wide BVH is deeper than the traversal stack");
+    auto align = [](size_t x) { return (x + 255) & ~size_t(255); };
+    const size_t off_nodes = 0;
+    const size_t off_sph = align(L.wide_nodes.size() * sizeof(DWideNode));
+    const size_t off_w2d = align(off_sph + L.wide_spheres.size() * sizeof(DSphere));
+    const size_t off_d2w = align(off_w2d + L.wide_to_dev.size() * sizeof(int32_t));
+    const size_t total = align(off_d2w + L.dev_to_wide.size() * sizeof(int32_t)) + 256;
+    std::vector<uint8_t> host(total, 0);
+    std::memcpy(host.data() + off_nodes, L.wide_nodes.data(), L.wide_nodes.size() * sizeof(DWideNode));
+    std::memcpy(host.data() + off_sph, L.wide_spheres.data(), L.wide_spheres.size() * sizeof(DSphere));
+    std::memcpy(host.data() + off_w2d, L.wide_to_dev.data(), L.wide_to_dev.size() * sizeof(int32_t));
+    std::memcpy(host.data() + off_d2w, L.dev_to_wide.data(), L.dev_to_wide.size() * sizeof(int32_t));
+    RT_CUDA(cudaSetDevice(ds->device));
+    RT_CUDA(cudaMalloc(&ds->wide_blob, total));
+    RT_CUDA(cudaMemcpy(ds->wide_blob, host.data(), total, cudaMemcpyHostToDevice));
+    ds->bytes += total;
+    uint8_t *base = static_cast<uint8_t *>(ds->wide_blob);
+    ds->g.wide_nodes = reinterpret_cast<const uint4 *>(base + off_nodes);
+    ds->g.wide_spheres = reinterpret_cast<const float4 *>(base + off_sph);
+    ds->g.wide_to_dev = reinterpret_cast<const int32_t *>(base + off_w2d);
+    ds->g.dev_to_wide = reinterpret_cast<const int32_t *>(base + off_d2w);
+    ds->wide_depth = L.wide_depth;
+    return RT_OK;
+}
+
+// which tree a frame walks: the binary one staged in shared memory when the scene fits there; otherwise (or on request)
+// the 8-wide compressed one from global memory; RT_FLAG_BVH2 keeps the binary tree for comparisons
+bool frame_walks_wide_tree(const DeviceScene *ds, int opt_flags, bool smem_fits) {
+    if (ds->g.n_bounded <= 0 || (opt_flags & RT_FLAG_BVH2)) return false;
+    if (opt_flags & RT_FLAG_WIDE_BVH) return true;
+    return !smem_fits || (opt_flags & RT_FLAG_NO_SMEM) ? ds->g.wide_nodes != nullptr : false;
+}
+int prepare_frame(RtScene *scene, const RtRenderOpts *opts) {
+    if (opts->flags & RT_FLAG_WIDE_BVH) return device_scene_ensure_wide(scene);
     return RT_OK;
 }
 
@@ -303,14 +348,14 @@ __device__ __forceinline__ void flush_counters(unsigned long long *counters, uin
 //                  remaining sample indices (Scene.fs:191-192).
 // A warp issues one instruction every ~7.6 cycles whatever the load, so the kernel ends one whole item after the
 // work runs out: hence chunks of decreasing length, the last ones a single sample (see build_chunks).
-template <bool PROBE, bool SMEM, bool COUNT, bool SSTACK>
+template <bool PROBE, bool SMEM, bool COUNT, bool SSTACK, bool WIDE>
 __global__ void __launch_bounds__(kBlockThreads, 1) render_kernel(const FrameParams fp) {
     const SceneAccess<SMEM> sc = stage_scene<SMEM>(fp);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     typename std::conditional<SSTACK, SharedStack, LocalStack>::type stack;
     if constexpr (SSTACK) {
         stack.base = uint32_t(__cvta_generic_to_shared(rtfs_smem)) + 16u * fp.s_stack + 4u * threadIdx.x;
-        stack.stride = 4u * blockDim.x;
+        stack.stride = 4u * blockDim.x; // words of one stack level (wide walk: two levels per entry)
     }
     WarpScratch *ws = reinterpret_cast<WarpScratch *>(rtfs_smem + fp.s_warp) + warp;
     unsigned long long *work = fp.counters + (PROBE ? CN_WORK_PROBE : CN_WORK_MAIN);
@@ -439,7 +484,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) render_kernel(const FramePar
             if (active) {
                 uint32_t result;
                 ++n_rays;
-                if (path_step<SMEM, COUNT>(ps, sc, fp.cam.depth, result, cn, tracing, stack)) {
+                if (path_step<SMEM, COUNT, decltype(stack), WIDE>(ps, sc, fp.cam.depth, result, cn, tracing, stack)) {
                     int *acc = &ws->slot[my].acc[0][0]; // PixelStats.add into the item's accumulators
                     atomicAdd(acc + lane_slot, int((result >> 16) & 255u));
                     atomicAdd(acc + 32 + lane_slot, int((result >> 8) & 255u));
@@ -534,17 +579,18 @@ struct LaunchPlan {
 };
 
 typedef void (*RenderKernelFn)(const FrameParams);
-template <bool PROBE, bool SMEM, bool SSTACK>
+template <bool PROBE, bool SMEM, bool SSTACK, bool WIDE>
 static RenderKernelFn pick_count(bool count) {
-    return count ? render_kernel<PROBE, SMEM, true, SSTACK> : render_kernel<PROBE, SMEM, false, SSTACK>;
+    return count ? render_kernel<PROBE, SMEM, true, SSTACK, WIDE> : render_kernel<PROBE, SMEM, false, SSTACK, WIDE>;
 }
-template <bool PROBE, bool SMEM>
-static RenderKernelFn pick_stack(bool sstack, bool count) {
-    return sstack ? pick_count<PROBE, SMEM, true>(count) : pick_count<PROBE, SMEM, false>(count);
+template <bool PROBE>
+static RenderKernelFn pick_global(bool sstack, bool wide, bool count) { // the scene is read from global memory
+    if (wide) return sstack ? pick_count<PROBE, false, true, true>(count) : pick_count<PROBE, false, false, true>(count);
+    return sstack ? pick_count<PROBE, false, true, false>(count) : pick_count<PROBE, false, false, false>(count);
 }
-static RenderKernelFn pick_kernel(bool probe, bool smem, bool count, bool sstack) {
-    if (probe) return smem ? pick_count<true, true, false>(count) : pick_stack<true, false>(sstack, count);
-    return smem ? pick_count<false, true, false>(count) : pick_stack<false, false>(sstack, count);
+static RenderKernelFn pick_kernel(bool probe, bool smem, bool count, bool sstack, bool wide) {
+    if (probe) return smem ? pick_count<true, true, false, false>(count) : pick_global<true>(sstack, wide, count);
+    return smem ? pick_count<false, true, false, false>(count) : pick_global<false>(sstack, wide, count);
 }
 
 // lays out shared memory and sizes the persistent grid
@@ -554,7 +600,8 @@ static int plan_launch(DeviceScene *ds, FrameParams &fp, bool probe, bool count,
     const size_t scene_q = nodes_q + sph_q + mat_q;
     // stage the scene in shared memory when it fits beside the per-warp scratch (one block per SM)
     bool smem = (scene_q + warp_q) * 16 + 1024 <= ds->ws->smem_optin && ds->g.n_bounded > 0;
-    if (no_smem) smem = false;
+    const bool wide = frame_walks_wide_tree(ds, fp.opt_flags, smem);
+    if (no_smem || wide) smem = false;
     fp.s_nodes = 0;
     fp.s_spheres = uint32_t(nodes_q);
     fp.s_mats = uint32_t(nodes_q + sph_q);
@@ -564,11 +611,11 @@ static int plan_launch(DeviceScene *ds, FrameParams &fp, bool probe, bool count,
     // (measured on the 100 k-sphere scene at 16 spp: 124.3 against 128.2 ms; with the scene itself in shared memory the
     // same change is within noise, 67.1 against 67.4 ms on C2, 137.7 against 136.7 on C4, so those kernels keep a local stack)
     const size_t used_q = (smem ? scene_q : 0) + warp_q;
-    const size_t stack_q = size_t(ds->max_depth + 1) * kBlockThreads * 4 / 16;
+    const size_t stack_q = size_t(wide ? 2 * (ds->wide_depth + 1) : ds->max_depth + 1) * kBlockThreads * 4 / 16;
     const bool sstack = !smem && ds->g.n_bounded > 0 && (used_q + stack_q) * 16 + 1024 <= ds->ws->smem_optin;
     fp.s_stack = uint32_t(used_q);
     plan.smem_bytes = (used_q + (sstack ? stack_q : 0)) * 16;
-    fn = pick_kernel(probe, smem, count, sstack);
+    fn = pick_kernel(probe, smem, count, sstack, wide);
     RT_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(plan.smem_bytes)));
     int per_sm = 0;
     RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)fn, kBlockThreads, plan.smem_bytes));
@@ -610,6 +657,7 @@ void fill_frame(FrameParams &fp, DeviceScene *ds, const RtCamera &cam, int max_w
         fp.sample_end = cam.samples_per_pixel;
     }
     fp.counters = ds->ws->d_counters;
+    fp.opt_flags = opts.flags;
 }
 
 // Cuts this rank's local sample range [0, n_local) into chunks: `bulk` samples per chunk, then a taper
@@ -765,6 +813,7 @@ int rt_device_probe(RtScene *scene, const RtCamera *camera, int32_t max_w, int32
     int rc = check_frame_args(scene, camera, max_w, max_h, opts);
     if (rc != RT_OK) return rc;
     if (world < 1 || rank < 0 || rank >= world || !d_stats || !d_flags) return fail(RT_ERR_INVALID_ARGUMENT, "rt_device_probe: bad rank/world/buffers");
+    if ((rc = prepare_frame(scene, opts)) != RT_OK) return rc;
     auto *ds = static_cast<DeviceScene *>(scene->dev);
     RT_CUDA(cudaSetDevice(ds->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -797,6 +846,7 @@ int rt_device_main(RtScene *scene, const RtCamera *camera, int32_t max_w, int32_
     int rc = check_frame_args(scene, camera, max_w, max_h, opts);
     if (rc != RT_OK) return rc;
     if (world < 1 || rank < 0 || rank >= world || !d_stats || !d_flags) return fail(RT_ERR_INVALID_ARGUMENT, "rt_device_main: bad rank/world/buffers");
+    if ((rc = prepare_frame(scene, opts)) != RT_OK) return rc;
     auto *ds = static_cast<DeviceScene *>(scene->dev);
     RT_CUDA(cudaSetDevice(ds->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -852,6 +902,7 @@ int rt_render(RtScene *scene, const RtCamera *camera, int32_t max_w, int32_t max
     if (!rgb_out) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render: rgb_out is null");
     if (opts->mode == RT_MODE_WAVEFRONT) return render_wavefront(scene, camera, max_w, max_h, opts, rgb_out, sums_out, stats);
     if (opts->mode != RT_MODE_MEGAKERNEL) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render: unknown mode");
+    if ((rc = prepare_frame(scene, opts)) != RT_OK) return rc;
     auto *ds = static_cast<DeviceScene *>(scene->dev);
     RT_CUDA(cudaSetDevice(ds->device));
     const size_t n_pixels = size_t(2 * max_w + 1) * size_t(2 * max_h + 1);

@@ -70,6 +70,8 @@ struct DeviceScene {
     DRefNode *ref_nodes = nullptr;
     int32_t n_ref_nodes = 0;
     void *blob = nullptr; // one allocation holding nodes | spheres | materials | unbounded | reference nodes | textures
+    void *wide_blob = nullptr; // the 8-wide compressed tree: nodes | spheres in its order | the two index maps
+    int32_t wide_depth = 0;
     std::vector<PooledTexture> images; // image textures borrowed from the pool
     size_t bytes = 0;
     int32_t max_depth = 0; // depth of the tree: the walk's stack never holds more entries
@@ -105,6 +107,7 @@ struct FrameParams {
     // shared-memory staging
     uint32_t s_nodes, s_spheres, s_mats, s_warp; // offsets in uint4 units
     uint32_t s_stack; // SSTACK kernels: the walk stacks, one column of `stack_levels` words per thread (uint4 units)
+    int32_t opt_flags; // RtRenderOpts.flags
 };
 
 
@@ -126,6 +129,9 @@ int check_frame_args(const RtScene *scene, const RtCamera *camera, int max_w, in
 void fill_frame(FrameParams &fp, DeviceScene *ds, const RtCamera &cam, int max_w, int max_h, const RtRenderOpts &opts, int rank, int world);
 int launch_probe(DeviceScene *ds, FrameParams fp, bool count, bool no_smem, cudaStream_t st, int *launches);
 int launch_main(DeviceScene *ds, FrameParams fp, const FlagsView &flags, bool count, bool no_smem, cudaStream_t st, int *launches);
+// makes sure the tree the frame will walk is on the device (the wide tree is built on first use for small scenes)
+int prepare_frame(RtScene *scene, const RtRenderOpts *opts);
+bool frame_walks_wide_tree(const DeviceScene *ds, int opt_flags, bool smem_fits);
 void read_counters(DeviceScene *ds, RtStats *stats, size_t n_pixels, bool adaptive);
 
 inline DevCamera make_dev_camera(const RtCamera &c, int max_w, int max_h) {

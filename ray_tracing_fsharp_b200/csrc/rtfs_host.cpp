@@ -407,6 +407,164 @@ void build_device_layout(const RtHittable *objs, int32_t n_objs, HostSceneLayout
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// 8-wide compressed BVH: greedy collapse of the SAH BVH2 (open the child of largest area until there are eight),
+// children placed in octant-ordered slots, boxes quantised outwards to 8 bits on a per-node power-of-two grid
+// ---------------------------------------------------------------------------------------------
+void build_wide_layout(HostSceneLayout &L) {
+    if (!L.wide_nodes.empty() || L.n_bounded < 1) return;
+    struct Child {
+        int32_t ref; // BVH2 ref: >= 0 internal node, < 0 leaf ~sphere
+        float mn[3], mx[3];
+    };
+    auto area = [](const Child &c) {
+        double dx = double(c.mx[0]) - c.mn[0], dy = double(c.mx[1]) - c.mn[1], dz = double(c.mx[2]) - c.mn[2];
+        return (dx < 0 || dy < 0 || dz < 0) ? 0.0 : dx * dy + dy * dz + dz * dx;
+    };
+    auto children_of = [&](int32_t node, std::vector<Child> &out) {
+        const DNode &nd = L.nodes[node];
+        Child l{nd.left, {nd.l_mn[0], nd.l_mn[1], nd.l_mn[2]}, {nd.l_mx[0], nd.l_mx[1], nd.l_mx[2]}};
+        Child r{nd.right, {nd.r_mn[0], nd.r_mn[1], nd.r_mn[2]}, {nd.r_mx[0], nd.r_mx[1], nd.r_mx[2]}};
+        out.push_back(l);
+        if (!(L.root_is_leaf && node == 0)) out.push_back(r); // a one-sphere scene: the right child is a never-entered dummy
+    };
+    // spheres below each BVH2 node: a subtree of at most kLeafMax spheres can sit in ONE leaf slot of a wide node
+    constexpr int kLeafMax = 3;
+    std::vector<int32_t> below(L.nodes.size(), 0);
+    for (int32_t i = int32_t(L.nodes.size()) - 1; i >= 0; --i) { // children have larger indices (DFS pre-order)
+        const DNode &nd = L.nodes[i];
+        below[i] = (nd.left < 0 ? 1 : below[nd.left]) + ((L.root_is_leaf && i == 0) ? 0 : (nd.right < 0 ? 1 : below[nd.right]));
+    }
+    auto count_of = [&](int32_t ref) { return ref < 0 ? 1 : below[ref]; };
+    std::vector<int32_t> gathered;
+    auto gather = [&](int32_t ref, auto &&self) -> void { // device ids of the spheres below `ref`, in tree order
+        if (ref < 0) {
+            gathered.push_back(~ref);
+            return;
+        }
+        self(L.nodes[ref].left, self);
+        if (!(L.root_is_leaf && ref == 0)) self(L.nodes[ref].right, self);
+    };
+    struct Work {
+        int32_t bvh2;
+        uint32_t index;
+        int32_t depth;
+    };
+    L.wide_nodes.assign(1, DWideNode{});
+    L.wide_spheres.clear();
+    L.wide_to_dev.clear();
+    std::vector<Work> work{{0, 0u, 1}};
+    for (size_t w = 0; w < work.size(); ++w) {
+        const Work job = work[w];
+        L.wide_depth = std::max(L.wide_depth, job.depth);
+        std::vector<Child> ch;
+        children_of(job.bvh2, ch);
+        // open the child of largest area until there are eight: first the subtrees too big for a leaf slot, then (slots
+        // permitting) the small ones, whose spheres then get boxes of their own
+        for (int pass = 0; pass < 2; ++pass)
+            while (ch.size() < 8) {
+                int pick = -1;
+                double best = -1.0;
+                for (size_t i = 0; i < ch.size(); ++i)
+                    if (ch[i].ref >= 0 && (pass == 1 || count_of(ch[i].ref) > kLeafMax) && area(ch[i]) > best) {
+                        best = area(ch[i]);
+                        pick = int(i);
+                    }
+                if (pick < 0) break;
+                const int32_t open = ch[pick].ref;
+                ch.erase(ch.begin() + pick);
+                children_of(open, ch);
+            }
+        const int n = int(ch.size());
+        float lo[3], hi[3];
+        for (int a = 0; a < 3; ++a) {
+            lo[a] = ch[0].mn[a];
+            hi[a] = ch[0].mx[a];
+            for (int i = 1; i < n; ++i) {
+                lo[a] = std::min(lo[a], ch[i].mn[a]);
+                hi[a] = std::max(hi[a], ch[i].mx[a]);
+            }
+        }
+        // octant-ordered slots: greedily give each (child, slot) pair of largest projection of the child's centre
+        // (relative to the node's) on the slot's diagonal
+        int slot_of[8], child_in[8];
+        std::fill(slot_of, slot_of + 8, -1);
+        std::fill(child_in, child_in + 8, -1);
+        double cost[8][8];
+        for (int i = 0; i < n; ++i)
+            for (int s = 0; s < 8; ++s) {
+                double c = 0.0;
+                for (int a = 0; a < 3; ++a) {
+                    double rel = 0.5 * (double(ch[i].mn[a]) + ch[i].mx[a]) - 0.5 * (double(lo[a]) + hi[a]);
+                    c += ((s >> (2 - a)) & 1) ? rel : -rel;
+                }
+                cost[i][s] = c;
+            }
+        for (int k = 0; k < n; ++k) {
+            int bi = -1, bs = -1;
+            for (int i = 0; i < n; ++i) {
+                if (slot_of[i] >= 0) continue;
+                for (int s = 0; s < 8; ++s)
+                    if (child_in[s] < 0 && (bi < 0 || cost[i][s] > cost[bi][bs])) {
+                        bi = i;
+                        bs = s;
+                    }
+            }
+            slot_of[bi] = bs;
+            child_in[bs] = bi;
+        }
+        DWideNode nd{};
+        int ebits[3];
+        double step[3];
+        for (int a = 0; a < 3; ++a) {
+            nd.p[a] = lo[a];
+            double ext = double(hi[a]) - double(lo[a]);
+            int e = ext > 0.0 ? int(std::ceil(std::log2(ext / 255.0))) : -100;
+            e = std::max(-100, std::min(100, e));
+            while (std::ldexp(255.0, e) < ext) ++e; // log2 rounding: the grid must span the node
+            ebits[a] = e;
+            step[a] = std::ldexp(1.0, e);
+            nd.e[a] = uint8_t(e + 127 + 15);
+        }
+        nd.child_base = uint32_t(L.wide_nodes.size());
+        nd.prim_base = uint32_t(L.wide_spheres.size());
+        int n_internal = 0, n_prims = 0;
+        for (int s = 0; s < 8; ++s) {
+            nd.qlo_x[s] = nd.qlo_y[s] = nd.qlo_z[s] = 255; // empty slot: an inverted box
+            nd.qhi_x[s] = nd.qhi_y[s] = nd.qhi_z[s] = 0;
+            const int i = child_in[s];
+            if (i < 0) continue;
+            uint8_t *qlo[3] = {nd.qlo_x, nd.qlo_y, nd.qlo_z}, *qhi[3] = {nd.qhi_x, nd.qhi_y, nd.qhi_z};
+            for (int a = 0; a < 3; ++a) {
+                double l = std::floor((double(ch[i].mn[a]) - double(lo[a])) / step[a]);
+                double h = std::ceil((double(ch[i].mx[a]) - double(lo[a])) / step[a]);
+                qlo[a][s] = uint8_t(std::max(0.0, std::min(255.0, l)));
+                qhi[a][s] = uint8_t(std::max(0.0, std::min(255.0, h)));
+            }
+            if (ch[i].ref >= 0 && count_of(ch[i].ref) > kLeafMax) {
+                nd.imask |= uint8_t(1u << s);
+                nd.meta[s] = uint8_t((1u << 5) | (24u + unsigned(s)));
+                work.push_back(Work{ch[i].ref, nd.child_base + uint32_t(n_internal), job.depth + 1});
+                ++n_internal;
+            } else { // a leaf slot: one to three spheres, the count in unary
+                gathered.clear();
+                gather(ch[i].ref, gather);
+                nd.meta[s] = uint8_t((((1u << gathered.size()) - 1u) << 5) | unsigned(n_prims));
+                for (int32_t dev : gathered) {
+                    L.wide_spheres.push_back(L.spheres[dev]);
+                    L.wide_to_dev.push_back(dev);
+                    ++n_prims;
+                }
+            }
+        }
+        (void)ebits;
+        L.wide_nodes.resize(L.wide_nodes.size() + n_internal);
+        L.wide_nodes[job.index] = nd;
+    }
+    L.dev_to_wide.assign(L.n_bounded, -1);
+    for (size_t k = 0; k < L.wide_to_dev.size(); ++k) L.dev_to_wide[L.wide_to_dev[k]] = int32_t(k);
+}
+
 // The reference-topology tree is only needed by the conformance traversal and by inspection; it is built on
 // first use (its median-split build sorts every range three times: half a second for 100 000 spheres).
 void scene_ensure_reference(RtScene *s) {
@@ -590,6 +748,7 @@ int rt_scene_create(const RtHittable *objects, int32_t n_objects, const RtTextur
         delete s;
         return fail(RT_ERR_UNSUPPORTED, "rt_scene_create: BVH deeper than the traversal stack");
     }
+    if (s->layout.n_bounded >= kWideBvhThreshold) build_wide_layout(s->layout); // what renders of a scene this size walk
     s->device = device;
     if (device >= 0) {
         int rc = device_scene_upload(s);
@@ -628,5 +787,73 @@ int rt_scene_bvh_nodes(const RtScene *scene, int32_t which, double *bounds, int3
     return RT_OK;
 }
 size_t rt_scene_device_bytes(const RtScene *scene) { return scene ? device_scene_bytes(scene) : 0; }
+
+// Builds (if need be) and checks the 8-wide compressed tree on the host: every bounded sphere sits in exactly one leaf
+// slot, and the decoded box of every slot contains all the spheres below it (each plane decoded as p + q 2^e).
+int rt_scene_wide_bvh_check(RtScene *scene, int32_t *n_nodes, int32_t *depth, int32_t *n_spheres, double *mean_children) {
+    if (!scene) return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_wide_bvh_check: null scene");
+    HostSceneLayout &L = scene->layout;
+    build_wide_layout(L);
+    std::vector<int> seen(size_t(L.n_bounded), 0);
+    size_t children = 0;
+    struct Item {
+        uint32_t node;
+        double mn[3], mx[3]; // what the ancestors' slots promise to contain
+        bool bounded;
+    };
+    std::vector<Item> todo;
+    if (!L.wide_nodes.empty()) todo.push_back(Item{0u, {0, 0, 0}, {0, 0, 0}, false});
+    while (!todo.empty()) {
+        Item it = todo.back();
+        todo.pop_back();
+        if (it.node >= L.wide_nodes.size()) return fail(RT_ERR_DEGENERATE, "wide BVH: child index out of range");
+        const DWideNode &nd = L.wide_nodes[it.node];
+        int internal = 0;
+        for (int s = 0; s < 8; ++s) {
+            if (nd.meta[s] == 0) continue;
+            ++children;
+            const uint8_t *qlo[3] = {nd.qlo_x, nd.qlo_y, nd.qlo_z}, *qhi[3] = {nd.qhi_x, nd.qhi_y, nd.qhi_z};
+            Item c{0u, {0, 0, 0}, {0, 0, 0}, true};
+            for (int a = 0; a < 3; ++a) {
+                double step = std::ldexp(1.0, int(nd.e[a]) - 127 - 15);
+                c.mn[a] = double(nd.p[a]) + qlo[a][s] * step;
+                c.mx[a] = double(nd.p[a]) + qhi[a][s] * step;
+                if (it.bounded) { // a child's box may stick out of its parent's by quantisation only if the content does not
+                    c.mn[a] = std::max(c.mn[a], it.mn[a]);
+                    c.mx[a] = std::min(c.mx[a], it.mx[a]);
+                }
+            }
+            const bool inner = (nd.imask >> s) & 1u;
+            if (inner) {
+                if (nd.meta[s] != uint8_t((1u << 5) | (24u + unsigned(s)))) return fail(RT_ERR_DEGENERATE, "wide BVH: bad meta of an internal slot");
+                c.node = nd.child_base + uint32_t(internal++);
+                todo.push_back(c);
+            } else {
+                int count = nd.meta[s] >> 5, off = nd.meta[s] & 31;
+                count = count == 1 ? 1 : (count == 3 ? 2 : (count == 7 ? 3 : -1));
+                if (count < 0 || off + count > 24) return fail(RT_ERR_DEGENERATE, "wide BVH: bad meta of a leaf slot");
+                for (int k = 0; k < count; ++k) {
+                    size_t w = size_t(nd.prim_base) + off + k;
+                    if (w >= L.wide_to_dev.size()) return fail(RT_ERR_DEGENERATE, "wide BVH: sphere index out of range");
+                    int32_t dev = L.wide_to_dev[w];
+                    if (dev < 0 || dev >= L.n_bounded || L.dev_to_wide[dev] != int32_t(w)) return fail(RT_ERR_DEGENERATE, "wide BVH: index maps disagree");
+                    ++seen[dev];
+                    const DSphere &sp = L.spheres[dev];
+                    const float c3[3] = {sp.cx, sp.cy, sp.cz};
+                    for (int a = 0; a < 3; ++a)
+                        if (double(c3[a]) - double(sp.r) < c.mn[a] || double(c3[a]) + double(sp.r) > c.mx[a])
+                            return fail(RT_ERR_DEGENERATE, "wide BVH: a sphere sticks out of a box above it");
+                }
+            }
+        }
+    }
+    for (int v : seen)
+        if (v != 1) return fail(RT_ERR_DEGENERATE, "wide BVH: a sphere is missing or duplicated");
+    if (n_nodes) *n_nodes = int32_t(L.wide_nodes.size());
+    if (depth) *depth = L.wide_depth;
+    if (n_spheres) *n_spheres = int32_t(L.wide_to_dev.size());
+    if (mean_children) *mean_children = L.wide_nodes.empty() ? 0.0 : double(children) / double(L.wide_nodes.size());
+    return RT_OK;
+}
 
 } // extern "C"

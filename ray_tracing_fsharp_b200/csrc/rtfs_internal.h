@@ -89,6 +89,28 @@ struct DRefNode {
 };
 static_assert(sizeof(DRefNode) == 32, "DRefNode must be 32 bytes");
 
+// 8-wide compressed BVH node (after Ylitie, Karras, Laine, "Efficient Incoherent Ray Traversal on GPUs Through
+// Compressed Wide BVHs", HPG 2017): 80 B = five 128-bit loads.  The eight child boxes are quantised to 8 bits per
+// plane on a per-node grid: coordinate q stands for p + q * 2^e (rounded outwards at build time).
+//   q0 = {p.x, p.y, p.z, ex' | ey' << 8 | ez' << 16 | imask << 24}   e' = e + 127 + 15: the bits of the float 2^(e+15) >> 23
+//   q1 = {child_base, prim_base, meta[0..3], meta[4..7]}
+//   q2 = {qlo.x[0..3], qlo.x[4..7], qlo.y[0..3], qlo.y[4..7]}
+//   q3 = {qlo.z[0..3], qlo.z[4..7], qhi.x[0..3], qhi.x[4..7]}
+//   q4 = {qhi.y[0..3], qhi.y[4..7], qhi.z[0..3], qhi.z[4..7]}
+// Children sit in slots 0..7; slot s is the child lying towards the octant with signs (x: bit 2, y: bit 1, z: bit 0), so
+// that `slot XOR octant-of-the-ray` orders the children roughly front to back without computing distances.
+// imask: which slots hold internal nodes; those are stored consecutively from child_base in slot order.
+// meta[s]: 0 = empty; internal node: 0b001 << 5 | (24 + s); leaf: (unary count of spheres) << 5 | offset from prim_base.
+struct DWideNode {
+    float p[3];
+    uint8_t e[3];
+    uint8_t imask;
+    uint32_t child_base, prim_base;
+    uint8_t meta[8];
+    uint8_t qlo_x[8], qlo_y[8], qlo_z[8], qhi_x[8], qhi_y[8], qhi_z[8];
+};
+static_assert(sizeof(DWideNode) == 80, "DWideNode must be 80 bytes");
+
 struct HostSceneLayout {
     // device primitive ids: [0, n_bounded) bounded spheres in SAH leaf order, then unbounded in array order
     std::vector<DSphere> spheres;
@@ -100,12 +122,23 @@ struct HostSceneLayout {
     int32_t n_bounded = 0;
     int32_t root_is_leaf = 0;
     int32_t max_depth = 0;
+    // the 8-wide compressed tree over the same spheres (build_wide_layout): its own sphere order (the spheres of a node
+    // are consecutive), mapped to and from device primitive ids
+    std::vector<DWideNode> wide_nodes;
+    std::vector<DSphere> wide_spheres;
+    std::vector<int32_t> wide_to_dev, dev_to_wide;
+    int32_t wide_depth = 0;
 };
 
 // SAH BVH2 over the bounded spheres with radius >= 0 (a bounded sphere with negative radius has an
 // inverted box and is never hit in the reference, F16).  Fills layout.spheres/nodes and the bounded
 // part of layout.materials; also exports the tree in HostNode form for inspection.
 void build_device_layout(const RtHittable *objs, int32_t n_objs, HostSceneLayout &layout, std::vector<HostNode> &sah_tree_out);
+// Collapses the SAH BVH2 of `layout` into the 8-wide compressed tree (fills layout.wide_*).  Idempotent.
+void build_wide_layout(HostSceneLayout &layout);
+// scenes with at least this many bounded spheres get the wide tree at rt_scene_create (it is what their renders use);
+// smaller ones build it on first use (RT_FLAG_WIDE_BVH)
+constexpr int32_t kWideBvhThreshold = 1024;
 
 } // namespace rtfs
 
@@ -126,6 +159,7 @@ namespace rtfs {
 void scene_ensure_reference(RtScene *scene);
 int device_scene_upload(RtScene *scene);
 int device_scene_ensure_reference(RtScene *scene);
+int device_scene_ensure_wide(RtScene *scene);
 void device_scene_free(RtScene *scene);
 size_t device_scene_bytes(const RtScene *scene);
 } // namespace rtfs

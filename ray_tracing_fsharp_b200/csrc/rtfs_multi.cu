@@ -212,6 +212,8 @@ int rt_multi_render(RtMulti *m, const RtCamera *camera, int32_t max_w, int32_t m
     const size_t n_pixels = size_t(2 * max_w + 1) * size_t(2 * max_h + 1);
     rc = multi_workspace(m, n_pixels, sums_out != nullptr);
     if (rc != RT_OK) return rc;
+    for (RtScene *s : m->scenes)
+        if ((rc = prepare_frame(s, opts)) != RT_OK) return rc;
     const bool count = (opts->flags & RT_FLAG_COUNTERS) != 0, no_smem = (opts->flags & RT_FLAG_NO_SMEM) != 0;
     std::vector<int> launches(world, 0);
     std::vector<FrameParams> fps(world);

@@ -41,6 +41,7 @@ def _declare(lib):
         "rt_scene_destroy": (None, [_vp]),
         "rt_scene_bvh_node_count": (C.c_int, [_vp, _i32]),
         "rt_scene_bvh_nodes": (C.c_int, [_vp, _i32, _vp, _vp, _vp]),
+        "rt_scene_wide_bvh_check": (C.c_int, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(C.c_double)]),
         "rt_scene_device_bytes": (C.c_size_t, [_vp]),
         "rt_scene_shared_memory_bytes": (C.c_size_t, [_vp]),
         "rt_render": (C.c_int, [_vp, C.POINTER(RtCamera), _i32, _i32, C.POINTER(RtRenderOpts), _vp, _vp, C.POINTER(RtStats)]),
@@ -183,6 +184,12 @@ class SceneHandle:
         if n:
             check(lib().rt_scene_bvh_nodes(self.ptr, which, ptr(bounds), ptr(right), ptr(prim)))
         return bounds, right, prim
+
+    def wide_bvh_check(self):
+        """Builds (if need be) and verifies the 8-wide compressed tree on the host; returns its figures."""
+        n, depth, ns, mc = _i32(), _i32(), _i32(), C.c_double()
+        check(lib().rt_scene_wide_bvh_check(self.ptr, C.byref(n), C.byref(depth), C.byref(ns), C.byref(mc)))
+        return {"nodes": n.value, "depth": depth.value, "spheres": ns.value, "mean_children": mc.value}
 
     def device_bytes(self):
         return int(lib().rt_scene_device_bytes(self.ptr))

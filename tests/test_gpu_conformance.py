@@ -207,10 +207,11 @@ def test_camera_rays(config):
 
 
 # ---- Scene.hitObject -----------------------------------------------------------------------------------------
-@pytest.mark.parametrize("traversal", [0, 1])
+@pytest.mark.parametrize("traversal", [0, 1, 2])
 @pytest.mark.parametrize("which", ["C2", "C4", "reduced"])
 def test_hit_object_matches_oracle(which, traversal):
-    """Scene.hitObject (Scene.fs:62-91): the closest primitive is IDENTICAL to the oracle's on every ray whose
+    """traversal 0: the binary SAH tree, ordered and culled; 1: the reference's own exhaustive DFS; 2: the 8-wide compressed tree.
+    Scene.hitObject (Scene.fs:62-91): the closest primitive is IDENTICAL to the oracle's on every ray whose
     double-precision margin exceeds FP32 rounding (helpers.fp32_safe_closest_hit: nothing grazed in front of the
     winner, no origin on a surface, winner leading the runner-up by > 1e-4); the filtered share is asserted small."""
     spec = small_random_spheres() if which == "reduced" else sample_images.CONFIGS[which]()

@@ -124,6 +124,46 @@ def test_wavefront_and_megakernel_agree_bit_for_bit(which):
         assert stb.launches > sta.launches
 
 
+def _mid_size_scene(n=6000):
+    spec = sample_images.many_spheres(n=n)
+    spec.max_width_coord, spec.max_height_coord, spec.spp = 64, 36, 24
+    return spec
+
+
+@pytest.mark.parametrize("which", ["reduced", "C2", "C4", "mid"])
+def test_wide_bvh_and_binary_bvh_agree_bit_for_bit(which):
+    """The 8-wide compressed tree (csrc/rtfs_core.cuh wide_closest; the default for scenes read from global memory) against
+    the binary SAH tree: the closest hit does not depend on the tree, so the same RNG keys and integer sums give identical
+    accumulators — with the binary tree staged in shared memory (small scenes), read from global memory, and on a scene
+    big enough (6000 spheres) that the wide tree is what an unflagged render walks."""
+    if which == "reduced":
+        spec = small_random_spheres()
+    elif which == "mid":
+        spec = _mid_size_scene()
+    else:
+        spec = _small(which, 48, 27, 24)
+    osc, dsc, cam = scene_pair(spec)
+    mw, mh = spec.max_width_coord, spec.max_height_coord
+    info = dsc.wide_bvh_check()
+    assert info["spheres"] == sum(1 for o in spec.objects if type(o).__name__ == "Sphere" and o.sphere.Radius >= 0)
+    for adaptive in (True, False):
+        a, sa, sta = dsc.render(cam, mw, mh, seed=43, adaptive=adaptive, want_sums=True, flags=abi.RT_FLAG_BVH2)
+        sa = sa.copy()
+        b, sb, stb = dsc.render(cam, mw, mh, seed=43, adaptive=adaptive, want_sums=True, flags=abi.RT_FLAG_WIDE_BVH)
+        assert np.array_equal(sa, sb)
+        assert int(sta.rays) == int(stb.rays) and int(sta.paths) == int(stb.paths)
+        c, sc_, stc = dsc.render(cam, mw, mh, seed=43, adaptive=adaptive, want_sums=True, flags=abi.RT_FLAG_WIDE_BVH | abi.RT_FLAG_COUNTERS)
+        assert np.array_equal(sa, sc_) and stc.box_tests > 0 and stc.prim_tests > 0
+        d, sd, std_ = dsc.render(cam, mw, mh, seed=43, adaptive=adaptive, want_sums=True)  # whatever the default is for this size
+        assert np.array_equal(sa, sd)
+        e, se, _ = dsc.render(cam, mw, mh, seed=43, adaptive=adaptive, want_sums=True, mode=abi.RT_MODE_WAVEFRONT)
+        assert np.array_equal(sa, se)
+    if which == "mid":  # and against the oracle, sample for sample (shared counter RNG)
+        ref, ref_stats, counters, _ = osc.render(cam, mw, mh, seed=43, rng_mode=1, adaptive=True)
+        rgb, sums, _ = dsc.render(cam, mw, mh, seed=43, adaptive=True, want_sums=True)
+        assert (rgb == ref).all(2).mean() > 0.97, (rgb == ref).all(2).mean()
+
+
 def test_hot_pink_when_the_bounce_budget_runs_out():
     """F3: a path that is still alive after maxCount + 1 interactions is HotPink, a miss is Black."""
     from ray_tracing_fsharp_b200.domain import Colour, Hittable, Pixel, Sphere, SphereStyle, Texture
