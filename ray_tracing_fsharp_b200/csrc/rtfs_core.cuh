@@ -22,6 +22,28 @@
 #define RTFS_HD __device__ __forceinline__
 #endif
 
+// Bounds checks on the traversal stacks and the item bookkeeping: always on in the host build that runs under ASan /
+// UBSan (host_debug/), and in a device build made with -DRTFS_DEBUG_BOUNDS (make bounds); compiled out otherwise.
+#if defined(RTFS_HOST_DEBUG)
+#define RTFS_BOUNDS(cond)                                                                                  \
+    do {                                                                                                   \
+        if (!(cond)) {                                                                                     \
+            std::fprintf(stderr, "rtfs bounds check failed: %s (%s:%d)\n", #cond, __FILE__, __LINE__);      \
+            std::abort();                                                                                  \
+        }                                                                                                  \
+    } while (0)
+#elif defined(RTFS_DEBUG_BOUNDS)
+#define RTFS_BOUNDS(cond)                                                                                  \
+    do {                                                                                                   \
+        if (!(cond)) {                                                                                     \
+            printf("rtfs bounds check failed: %s (%s:%d)\n", #cond, __FILE__, __LINE__);                   \
+            __trap();                                                                                      \
+        }                                                                                                  \
+    } while (0)
+#else
+#define RTFS_BOUNDS(cond) ((void)0)
+#endif
+
 namespace rtfs {
 
 constexpr float kTolF = 1e-8f;   // Float.tolerance, RayTracing/Float.fs:80
@@ -465,29 +487,50 @@ struct TraversalCounters {
 // has room for tree depth x block size words) a column of shared memory per thread.  Thread t's entry i sits at word
 // i * blockDim + t: lanes are always in distinct banks, whatever their depths, so a push or pop is one conflict-free
 // wavefront, where lanes at different depths of a local-memory stack touch a cache line each.
+constexpr int kLocalStackWords = 64;
 struct LocalStack {
-    int a[64];
-    RTFS_HD void put(int i, int v) { a[i] = v; }
-    RTFS_HD int get(int i) const { return a[i]; }
+    int a[kLocalStackWords];
+    RTFS_HD void put(int i, int v) {
+        RTFS_BOUNDS(i >= 0 && i < kLocalStackWords);
+        a[i] = v;
+    }
+    RTFS_HD int get(int i) const {
+        RTFS_BOUNDS(i >= 0 && i < kLocalStackWords);
+        return a[i];
+    }
     // two-word entries (the wide walk's node groups)
-    RTFS_HD void put2(int i, uint2 v) { a[2 * i] = int(v.x); a[2 * i + 1] = int(v.y); }
-    RTFS_HD uint2 get2(int i) const { return make_uint2(uint32_t(a[2 * i]), uint32_t(a[2 * i + 1])); }
+    RTFS_HD void put2(int i, uint2 v) {
+        RTFS_BOUNDS(i >= 0 && 2 * i + 1 < kLocalStackWords);
+        a[2 * i] = int(v.x);
+        a[2 * i + 1] = int(v.y);
+    }
+    RTFS_HD uint2 get2(int i) const {
+        RTFS_BOUNDS(i >= 0 && 2 * i + 1 < kLocalStackWords);
+        return make_uint2(uint32_t(a[2 * i]), uint32_t(a[2 * i + 1]));
+    }
 };
 #ifdef __CUDACC__
 struct SharedStack {
     uint32_t base, stride; // byte address of this thread's entry 0 in the shared window; bytes between entries
-    __device__ __forceinline__ void put(int i, int v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(base + uint32_t(i) * stride), "r"(v)); }
+    int levels;            // words per thread (checked with -DRTFS_DEBUG_BOUNDS only)
+    __device__ __forceinline__ void put(int i, int v) {
+        RTFS_BOUNDS(i >= 0 && i < levels);
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(base + uint32_t(i) * stride), "r"(v));
+    }
     __device__ __forceinline__ int get(int i) const {
+        RTFS_BOUNDS(i >= 0 && i < levels);
         int v;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base + uint32_t(i) * stride));
         return v;
     }
     __device__ __forceinline__ void put2(int i, uint2 v) {
+        RTFS_BOUNDS(i >= 0 && 2 * i + 1 < levels);
         const uint32_t a = base + uint32_t(2 * i) * stride;
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v.x));
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(a + stride), "r"(v.y));
     }
     __device__ __forceinline__ uint2 get2(int i) const {
+        RTFS_BOUNDS(i >= 0 && 2 * i + 1 < levels);
         const uint32_t a = base + uint32_t(2 * i) * stride;
         uint2 v;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v.x) : "r"(a));
@@ -553,7 +596,7 @@ RTFS_HD bool bvh_visit(const SceneAccess<SMEM> &sc, const RaySlabs &rs, float3 o
 // Refs here: a sphere is named ~k with k its index in the WIDE sphere order (wide_to_dev maps it to the device id).
 #ifdef __CUDACC__
 RTFS_HD float wide_plane(uint32_t q4, int j) { // byte j of q4 -> 1 + b 2^-15
-    return __uint_as_float(__byte_perm(q4, 0x3F800000u, 0x7640u | (uint32_t(j) << 4)));
+    return __uint_as_float(__byte_perm(q4, 0x3F800000u, 0x7604u | (uint32_t(j) << 4)));
 }
 RTFS_HD uint32_t sign_extend_s8x4(uint32_t x) { return __byte_perm(x, 0u, 0xba98u); }
 RTFS_HD uint4 ldg128(const uint4 *p) { return __ldg(p); }

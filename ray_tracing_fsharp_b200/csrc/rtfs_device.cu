@@ -356,6 +356,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) render_kernel(const FramePar
     if constexpr (SSTACK) {
         stack.base = uint32_t(__cvta_generic_to_shared(rtfs_smem)) + 16u * fp.s_stack + 4u * threadIdx.x;
         stack.stride = 4u * blockDim.x; // words of one stack level (wide walk: two levels per entry)
+        stack.levels = fp.stack_levels;
     }
     WarpScratch *ws = reinterpret_cast<WarpScratch *>(rtfs_smem + fp.s_warp) + warp;
     unsigned long long *work = fp.counters + (PROBE ? CN_WORK_PROBE : CN_WORK_MAIN);
@@ -485,6 +486,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) render_kernel(const FramePar
                 uint32_t result;
                 ++n_rays;
                 if (path_step<SMEM, COUNT, decltype(stack), WIDE>(ps, sc, fp.cam.depth, result, cn, tracing, stack)) {
+                    RTFS_BOUNDS(my >= 0 && my < kItemSlots && lane_slot >= 0 && lane_slot < 32);
                     int *acc = &ws->slot[my].acc[0][0]; // PixelStats.add into the item's accumulators
                     atomicAdd(acc + lane_slot, int((result >> 16) & 255u));
                     atomicAdd(acc + 32 + lane_slot, int((result >> 8) & 255u));
@@ -614,6 +616,7 @@ static int plan_launch(DeviceScene *ds, FrameParams &fp, bool probe, bool count,
     const size_t stack_q = size_t(wide ? 2 * (ds->wide_depth + 1) : ds->max_depth + 1) * kBlockThreads * 4 / 16;
     const bool sstack = !smem && ds->g.n_bounded > 0 && (used_q + stack_q) * 16 + 1024 <= ds->ws->smem_optin;
     fp.s_stack = uint32_t(used_q);
+    fp.stack_levels = int32_t(stack_q * 16 / (kBlockThreads * 4));
     plan.smem_bytes = (used_q + (sstack ? stack_q : 0)) * 16;
     fn = pick_kernel(probe, smem, count, sstack, wide);
     RT_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(plan.smem_bytes)));
