@@ -129,9 +129,9 @@ typedef struct RtRenderOpts {
 /* RtRenderOpts.flags */
 #define RT_FLAG_COUNTERS 1 /* also count the device traversal's box / primitive tests (slower kernel variant) */
 #define RT_FLAG_NO_SMEM 2  /* read the BVH from global memory even when it would fit in shared memory      */
-#define RT_FLAG_WIDE_BVH 4 /* walk the 8-wide compressed tree (global memory) whatever the scene's size; the default
-                              for scenes too large for shared memory                                           */
-#define RT_FLAG_BVH2 8     /* walk the binary tree even where the wide one is the default (A/B comparisons)   */
+#define RT_FLAG_WIDE_BVH 4 /* walk the 8-wide compressed tree (read from global memory) instead of the binary one:
+                              measured slower on B200 for every scene tried, kept selectable          */
+#define RT_FLAG_BVH2 8     /* walk the binary tree (the default; overrides RT_FLAG_WIDE_BVH)                      */
 
 typedef struct RtStats {
     uint64_t paths;     /* traceOnce calls (Scene.fs:118)                                        */

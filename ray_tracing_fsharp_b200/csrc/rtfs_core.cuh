@@ -598,16 +598,9 @@ RTFS_HD bool bvh_visit(const SceneAccess<SMEM> &sc, const RaySlabs &rs, float3 o
 RTFS_HD float wide_plane(uint32_t q4, int j) { // byte j of q4 -> 1 + b 2^-15
     return __uint_as_float(__byte_perm(q4, 0x3F800000u, 0x7604u | (uint32_t(j) << 4)));
 }
-RTFS_HD uint32_t sign_extend_s8x4(uint32_t x) { return __byte_perm(x, 0u, 0xba98u); }
 RTFS_HD uint4 ldg128(const uint4 *p) { return __ldg(p); }
 #else
 RTFS_HD float wide_plane(uint32_t q4, int j) { return 1.0f + float((q4 >> (8 * j)) & 255u) * 3.0517578125e-05f; }
-RTFS_HD uint32_t sign_extend_s8x4(uint32_t x) {
-    uint32_t r = 0;
-    for (int j = 0; j < 4; ++j)
-        if ((x >> (8 * j + 7)) & 1u) r |= 0xffu << (8 * j);
-    return r;
-}
 RTFS_HD uint4 ldg128(const uint4 *p) { return *p; }
 RTFS_HD int __clz(uint32_t x) { return x ? __builtin_clz(x) : 32; }
 RTFS_HD int __popc(uint32_t x) { return __builtin_popcount(x); }
@@ -648,7 +641,7 @@ RTFS_HD void wide_closest(const SceneGlobal &g, float3 o, float3 d, int last_ref
         for (int half = 0; half < 2; ++half) {
             const uint32_t meta4 = half ? n1.w : n1.z;
             const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-            const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
+            const uint32_t inner_mask4 = (is_inner4 >> 4) * 0xffu; // 0xff in the bytes of internal children (no carries: 1 * 0xff)
             const uint32_t bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1F1F1F1Fu;
             const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
             const uint32_t qlx = half ? n2.y : n2.x, qly = half ? n2.w : n2.z, qlz = half ? n3.y : n3.x;

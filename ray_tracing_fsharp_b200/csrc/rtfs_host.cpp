@@ -748,7 +748,6 @@ int rt_scene_create(const RtHittable *objects, int32_t n_objects, const RtTextur
         delete s;
         return fail(RT_ERR_UNSUPPORTED, "rt_scene_create: BVH deeper than the traversal stack");
     }
-    if (s->layout.n_bounded >= kWideBvhThreshold) build_wide_layout(s->layout); // what renders of a scene this size walk
     s->device = device;
     if (device >= 0) {
         int rc = device_scene_upload(s);

@@ -136,9 +136,7 @@ struct HostSceneLayout {
 void build_device_layout(const RtHittable *objs, int32_t n_objs, HostSceneLayout &layout, std::vector<HostNode> &sah_tree_out);
 // Collapses the SAH BVH2 of `layout` into the 8-wide compressed tree (fills layout.wide_*).  Idempotent.
 void build_wide_layout(HostSceneLayout &layout);
-// scenes with at least this many bounded spheres get the wide tree at rt_scene_create (it is what their renders use);
-// smaller ones build it on first use (RT_FLAG_WIDE_BVH)
-constexpr int32_t kWideBvhThreshold = 1024;
+// (built on first use: a render with RT_FLAG_WIDE_BVH, rt_test_hit_object(traversal = 2), rt_scene_wide_bvh_check)
 
 } // namespace rtfs
 

@@ -134,8 +134,8 @@ def _mid_size_scene(n=6000):
 def test_wide_bvh_and_binary_bvh_agree_bit_for_bit(which):
     """The 8-wide compressed tree (csrc/rtfs_core.cuh wide_closest; the default for scenes read from global memory) against
     the binary SAH tree: the closest hit does not depend on the tree, so the same RNG keys and integer sums give identical
-    accumulators — with the binary tree staged in shared memory (small scenes), read from global memory, and on a scene
-    big enough (6000 spheres) that the wide tree is what an unflagged render walks."""
+    accumulators — with the binary tree staged in shared memory (small scenes) and read from global memory (a scene of
+    6000 spheres, too big for shared memory)."""
     if which == "reduced":
         spec = small_random_spheres()
     elif which == "mid":
@@ -154,7 +154,7 @@ def test_wide_bvh_and_binary_bvh_agree_bit_for_bit(which):
         assert int(sta.rays) == int(stb.rays) and int(sta.paths) == int(stb.paths)
         c, sc_, stc = dsc.render(cam, mw, mh, seed=43, adaptive=adaptive, want_sums=True, flags=abi.RT_FLAG_WIDE_BVH | abi.RT_FLAG_COUNTERS)
         assert np.array_equal(sa, sc_) and stc.box_tests > 0 and stc.prim_tests > 0
-        d, sd, std_ = dsc.render(cam, mw, mh, seed=43, adaptive=adaptive, want_sums=True)  # whatever the default is for this size
+        d, sd, std_ = dsc.render(cam, mw, mh, seed=43, adaptive=adaptive, want_sums=True)  # the default: binary, shared memory if it fits
         assert np.array_equal(sa, sd)
         e, se, _ = dsc.render(cam, mw, mh, seed=43, adaptive=adaptive, want_sums=True, mode=abi.RT_MODE_WAVEFRONT)
         assert np.array_equal(sa, se)
