@@ -73,8 +73,12 @@ __global__ void k_plane_hit(int n, const float *o, const float *d, const double 
     u.p[0] = p[3 * i]; u.p[1] = p[3 * i + 1]; u.p[2] = p[3 * i + 2];
     u.n[0] = nrm[3 * i]; u.n[1] = nrm[3 * i + 1]; u.n[2] = nrm[3 * i + 2];
     u.shape = RT_SHAPE_INFINITE_PLANE;
+    // classify_unbounded's rule for planes (rtfs_host.cpp), so that each vector takes the path a scene object would
+    const double k = double(u.n[0]) * u.p[0] + double(u.n[1]) * u.p[1] + double(u.n[2]) * u.p[2];
+    u.fp32 = fabs(k) <= 16.0 ? 1 : 0;
+    u.k = float(k);
     float t;
-    bool hit = plane_hit_big(d3(ld3(o, i)), d3(ld3(d, i)), u, false, t);
+    bool hit = u.fp32 ? plane_hit_big_f32(ld3(o, i), ld3(d, i), u, false, t) : plane_hit_big(d3(ld3(o, i)), d3(ld3(d, i)), u, false, t);
     t_out[i] = hit ? t : CUDART_NAN_F;
 }
 __global__ void k_aabb_hit(int n, const float *o, const float *d, const float *mn, const float *mx, uint8_t *out) {

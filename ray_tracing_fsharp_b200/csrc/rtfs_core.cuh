@@ -345,6 +345,63 @@ RTFS_HD bool sphere_hit_big(D3 o, D3 d, double a, const DUnbounded &s, bool self
     t_out = ip;
     return ip > kTolF;
 }
+// The same sphere from the expanded quadratic, all FP32 (DUnbounded.fp32 = 1): c = |o|^2 - 2 o.C + k with k = |C|^2 - r^2
+// from the host, b = d.o - d.C.  No term is larger than scene-size x sphere-size, and nothing of the size of the
+// sphere squared is ever subtracted from its like.  Root selection as above.
+RTFS_HD float big_sphere_c(float3 o, const DUnbounded &s) {
+    const float3 C = f3(s.n[0], s.n[1], s.n[2]);
+    return fmaf(-2.0f, dot(o, C), dot(o, o)) + s.k;
+}
+RTFS_HD bool sphere_hit_big_f32(float3 o, float3 d, float a, const DUnbounded &s, bool self, float &t_out) {
+    const float3 C = f3(s.n[0], s.n[1], s.n[2]);
+    const float bf = dot(d, o) - dot(d, C);
+    const float inv_a = rcp_fast(a); // a = d.d ~ 1
+    if (self) { // c = 0: roots 0 and -2b / a; the reference keeps the one that is `positive`
+        float t = -2.0f * bf * inv_a;
+        t_out = t;
+        return t > kTolF;
+    }
+    const float cf = big_sphere_c(o, s);
+    const float disc = fmaf(bf, bf, -a * cf);
+    float ip;
+    if (fabsf(disc) < kTolF) { // Float.compare disc 0 = Equal
+        ip = -bf * inv_a;
+    } else if (disc < 0.0f) {
+        return false;
+    } else {
+        float im = sqrt_fast(disc); // disc >= 1e-8 here
+        float q1 = im - bf, q2 = -(bf + im); // i1 = q1 / a (the larger root), i2 = q2 / a; q1 * q2 = a * c
+        float i1, i2;
+        if (bf < 0.0f) { // |q1| >= im >= 1e-4
+            i1 = q1 * inv_a;
+            i2 = cf * rcp_fast(q1);
+        } else { // |q2| >= im >= 1e-4
+            i2 = q2 * inv_a;
+            i1 = cf * rcp_fast(q2);
+        }
+        bool p1 = i1 > kTolF, p2 = i2 > kTolF;
+        if (p1 && p2)
+            ip = (fabsf(i1 - i2) < kTolF || i1 < i2) ? i1 : i2;
+        else if (p1)
+            ip = i1;
+        else if (p2)
+            ip = i2;
+        else
+            return false;
+    }
+    t_out = ip;
+    return ip > kTolF;
+}
+// and the plane: n.(p0 - o) = k - n.o
+RTFS_HD bool plane_hit_big_f32(float3 o, float3 d, const DUnbounded &p, bool self, float &t_out) {
+    if (self) return false;
+    const float3 n = f3(p.n[0], p.n[1], p.n[2]);
+    const float den = dot(n, d);
+    if (fabsf(den) < kTolF) return false;
+    float t = (p.k - dot(n, o)) * rcp_fast(den); // |den| >= 1e-8
+    t_out = t;
+    return t > kTolF;
+}
 // InfinitePlane.intersection (InfinitePlane.fs:125-136): numerator and denominator in FP64, quotient in FP32
 RTFS_HD bool plane_hit_big(D3 o, D3 d, const DUnbounded &p, bool self, float &t_out) {
     if (self) return false; // the numerator is 0 on the plane: t = 0 is never `positive`
@@ -707,13 +764,18 @@ RTFS_HD Hit finish_hit(const SceneAccess<SMEM> &sc, float3 o, float3 d, int last
     const int last = last_ref;
     int best = best_ref;
     if (sc.g.n_unbounded > 0) {
-        const D3 od = d3(o), dd = d3(d);
-        const double a = dot(dd, dd);
+        const float af = dot(d, d);
         for (int i = 0; i < sc.g.n_unbounded; ++i) {
             const DUnbounded &u = sc.g.unb[i];
             float t;
             bool self = (sc.g.n_bounded + i) == last;
-            bool hit = (u.shape == RT_SHAPE_INFINITE_PLANE) ? plane_hit_big(od, dd, u, self, t) : sphere_hit_big(od, dd, a, u, self, t);
+            bool hit;
+            if (u.fp32) { // warp-uniform: every lane is at object i
+                hit = (u.shape == RT_SHAPE_INFINITE_PLANE) ? plane_hit_big_f32(o, d, u, self, t) : sphere_hit_big_f32(o, d, af, u, self, t);
+            } else {
+                const D3 od = d3(o), dd = d3(d);
+                hit = (u.shape == RT_SHAPE_INFINITE_PLANE) ? plane_hit_big(od, dd, u, self, t) : sphere_hit_big(od, dd, dot(dd, dd), u, self, t);
+            }
             if (COUNT) cn.prim_tests += 1;
             // Float.compare (t * t) bestFloat = Less, Scene.fs:82
             if (hit && fcmp(t * t, best_t * best_t) == CMP_LESS) {
@@ -787,12 +849,17 @@ RTFS_HD Hit closest_hit_reference(const DRefNode *ref_nodes, int n_ref_nodes, co
     }
     const D3 od = d3(o), dd = d3(d);
     const double a = dot(dd, dd);
+    const float af = dot(d, d);
     if (best == kNoPrim) best_t = kNoHitT;
     for (int i = 0; i < g.n_unbounded; ++i) {
         const DUnbounded &u = g.unb[i];
         float t;
         bool self = (g.n_bounded + i) == last;
-        bool hit = (u.shape == RT_SHAPE_INFINITE_PLANE) ? plane_hit_big(od, dd, u, self, t) : sphere_hit_big(od, dd, a, u, self, t);
+        bool hit;
+        if (u.fp32)
+            hit = (u.shape == RT_SHAPE_INFINITE_PLANE) ? plane_hit_big_f32(o, d, u, self, t) : sphere_hit_big_f32(o, d, af, u, self, t);
+        else
+            hit = (u.shape == RT_SHAPE_INFINITE_PLANE) ? plane_hit_big(od, dd, u, self, t) : sphere_hit_big(od, dd, a, u, self, t);
         if (hit && fcmp(t * t, best_t * best_t) == CMP_LESS) {
             best_t = t;
             best = g.n_bounded + i;
@@ -919,12 +986,21 @@ RTFS_HD ScatterResult scatter(const SceneAccess<SMEM> &sc, int prim, int last, f
             where = (prim == last) ? CMP_EQUAL : fcmp(dot(co, co), s.w * s.w);
         } else {
             const DUnbounded &u = sc.g.unb[prim - sc.g.n_bounded];
-            D3 c{u.p[0], u.p[1], u.p[2]};
-            D3 v = d3(strike) - c;
-            float3 vf = f3(float(v.x), float(v.y), float(v.z)); // the subtraction is what needs FP64 (|c| ~ 1000)
-            if (!unitise(vf, n)) return SCATTER_ERROR;
-            D3 co = c - d3(o);
-            where = (prim == last) ? CMP_EQUAL : fcmp(dot(co, co), u.r2);
+            if (u.fp32) {
+                // strike - C rounds at the size of the sphere (~6e-5 for r = 1000): 6e-8 of the normal's direction;
+                // inside / outside is the sign of the expanded |o - C|^2 - r^2 (Float.compare's 1e-8 band kept)
+                float3 vf = f3(strike.x - u.n[0], strike.y - u.n[1], strike.z - u.n[2]);
+                if (!unitise(vf, n)) return SCATTER_ERROR;
+                const float c = big_sphere_c(o, u);
+                where = (prim == last || fabsf(c) < kTolF) ? CMP_EQUAL : (c < 0.0f ? CMP_LESS : CMP_GREATER);
+            } else {
+                D3 c{u.p[0], u.p[1], u.p[2]};
+                D3 v = d3(strike) - c;
+                float3 vf = f3(float(v.x), float(v.y), float(v.z)); // the subtraction is what needs FP64 (|c| ~ 1000)
+                if (!unitise(vf, n)) return SCATTER_ERROR;
+                D3 co = c - d3(o);
+                where = (prim == last) ? CMP_EQUAL : fcmp(dot(co, co), u.r2);
+            }
         }
         if (where != CMP_GREATER) {
             if (!flipped) { inside = true; n = -n; }

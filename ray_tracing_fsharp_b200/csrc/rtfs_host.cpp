@@ -331,6 +331,33 @@ void export_sah(const HostSceneLayout &L, const std::vector<int32_t> &leaf_obj, 
 }
 } // namespace
 
+// FP32 (expanded form) or FP64 for an unbounded object — see DUnbounded.  The expanded forms lose accuracy only through
+// the size of k next to the quantity wanted (2 r h for a ray origin at height h above a sphere, h for a plane): absolute
+// error ~ 6e-8 (|o|^2 + 2 |o.c| + |k|).  With origins inside a scene of extent ~100 that is below 1e-6 in h when the
+// sphere is at least as big as its distance from the world origin (|c| <= |r|, r >= 8: floors, domes) and for planes
+// with |n.p0| <= 16; everything else keeps the FP64 path.
+void classify_unbounded(DUnbounded &u) {
+    u.fp32 = 0;
+    u.k = 0.f;
+    bool exact = true;
+    for (int a = 0; a < 3; ++a) exact = exact && double(float(u.p[a])) == u.p[a];
+    if (u.shape == RT_SHAPE_INFINITE_PLANE) {
+        double k = double(u.n[0]) * u.p[0] + double(u.n[1]) * u.p[1] + double(u.n[2]) * u.p[2];
+        if (std::fabs(k) <= 16.0) {
+            u.fp32 = 1;
+            u.k = float(k);
+        }
+        return;
+    }
+    double c2 = u.p[0] * u.p[0] + u.p[1] * u.p[1] + u.p[2] * u.p[2];
+    double r = std::fabs(double(u.r));
+    if (exact && r >= 8.0 && c2 <= r * r * 1.0000001 && double(u.r) * double(u.r) == u.r2) {
+        u.fp32 = 1;
+        u.k = float(c2 - u.r2);
+        for (int a = 0; a < 3; ++a) u.n[a] = float(u.p[a]);
+    }
+}
+
 void build_device_layout(const RtHittable *objs, int32_t n_objs, HostSceneLayout &L, std::vector<HostNode> &sah_tree_out) {
     L = HostSceneLayout{};
     sah_tree_out.clear();
@@ -392,6 +419,7 @@ void build_device_layout(const RtHittable *objs, int32_t n_objs, HostSceneLayout
         u.r2 = h.radius * h.radius; // Sphere.make, Sphere.fs:326
         u.r = float(h.radius);
         u.shape = h.shape;
+        classify_unbounded(u);
         device_id_of[i] = L.n_bounded + int32_t(L.unbounded.size());
         L.unbounded.push_back(u);
         L.materials.push_back(make_material(h, i));

@@ -57,16 +57,25 @@ struct DMaterial {
 static_assert(sizeof(DMaterial) == 32, "DMaterial must be 32 bytes");
 
 // Unbounded objects (UnboundedSphere, InfinitePlane), tested linearly after the tree (Scene.fs:77-86).
-// Geometry is kept in FP64: the translation o - c and the c-term of the quadratic are evaluated in
-// FP64 on the device because these spheres are typically huge (r = 1000, 2000) and FP32 cancels.
+// These spheres are typically huge (r = 1000, 2000), and |o - c|^2 - r^2 evaluated from o - c cancels catastrophically
+// in FP32.  Two evaluations (classify_unbounded picks per object, on the host):
+//   fp32 = 1  the EXPANDED forms  |o|^2 - 2 o.c + k  (k = |c|^2 - r^2)  and  k - n.o  (k = n.p0), k computed in FP64
+//             and rounded once: every term is then of the size of the scene, not of the sphere, and FP32 keeps
+//             ~1e-7 relative accuracy on the result.  Used when the centre is exactly representable in FP32 and k is
+//             small enough next to the scene (see classify_unbounded) — the floor, the sky dome, planes near the origin;
+//   fp32 = 0  the FP64 evaluation of exactly the cancelling terms (any other object).
 struct DUnbounded {
     double p[3];   // centre / point on plane
     double r2;     // radius^2 (sphere)
-    float n[3];    // plane normal
+    float n[3];    // plane: normal; sphere with fp32 = 1: the centre as floats (exactly p)
     float r;       // signed radius (sphere)
     int32_t shape; // RT_SHAPE_UNBOUNDED_SPHERE | RT_SHAPE_INFINITE_PLANE
-    int32_t pad[3];
+    int32_t fp32;
+    float k;       // sphere: |c|^2 - r^2; plane: n . p0
+    int32_t pad;
 };
+// fills fp32 / k (and n for spheres) of an object whose p, r, r2, n, shape are set
+void classify_unbounded(DUnbounded &u);
 static_assert(sizeof(DUnbounded) == 64, "DUnbounded must be 64 bytes");
 
 struct DTexture {
