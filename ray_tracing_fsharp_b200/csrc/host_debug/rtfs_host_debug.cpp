@@ -139,6 +139,10 @@ DevCamera dev_camera(const RtCamera &c, int max_w, int max_h) { // = make_dev_ca
     return d;
 }
 
+// optional trace of the work per ray (slab tests, primitive tests), path by path: feeds the warp-scheduling
+// simulations under profiles/ (how much of a warp's time is lost to the longest walk of its 32 lanes)
+std::vector<uint32_t> *g_ray_log = nullptr;
+
 template <bool WIDE>
 uint32_t trace_one(const SceneAccess<false> &sc, const DevCamera &cam, uint64_t seed, int r, int c, uint32_t sample, uint64_t &rays) {
     PathState ps;
@@ -148,7 +152,10 @@ uint32_t trace_one(const SceneAccess<false> &sc, const DevCamera &cam, uint64_t 
     if (!path_begin(ps, cam, uint32_t(seed), uint32_t(seed >> 32), r, c, sample)) return kBlack;
     for (;;) {
         ++rays;
-        if (path_step<false, true, LocalStack, WIDE>(ps, sc, cam.depth, result, cn, 1u, stack)) break;
+        const TraversalCounters before = cn;
+        const bool done = path_step<false, true, LocalStack, WIDE>(ps, sc, cam.depth, result, cn, 1u, stack);
+        if (g_ray_log) g_ray_log->push_back(((cn.box_tests - before.box_tests) << 8) | ((cn.prim_tests - before.prim_tests) & 255u) | (done ? 0x80000000u : 0u));
+        if (done) break;
     }
     return result;
 }
@@ -194,6 +201,20 @@ int dbg_render(const RtHittable *objects, int n_objects, const RtTexture *textur
     if (rays_out) *rays_out = rays;
     rt_scene_destroy(hs.scene);
     return RT_OK;
+}
+
+// dbg_render with a log of the work of every ray: log_out[i] = box tests << 8 | primitive tests, bit 31 = last ray of its path
+int dbg_render_logged(const RtHittable *objects, int n_objects, const RtTexture *textures, int n_textures, const RtCamera *camera, int max_w,
+                      int max_h, uint64_t seed, int adaptive, int wide, uint8_t *rgb_out, int32_t *sums_out, uint32_t *log_out, uint64_t log_cap,
+                      uint64_t *log_len) {
+    std::vector<uint32_t> log;
+    g_ray_log = &log;
+    uint64_t rays = 0;
+    int rc = dbg_render(objects, n_objects, textures, n_textures, camera, max_w, max_h, seed, adaptive, wide, rgb_out, sums_out, &rays);
+    g_ray_log = nullptr;
+    *log_len = log.size();
+    std::memcpy(log_out, log.data(), sizeof(uint32_t) * std::min<uint64_t>(log_cap, log.size()));
+    return rc;
 }
 
 // hitObject through both trees for explicit rays: prim_out = index into the caller's Hittable array, or -1
