@@ -41,6 +41,7 @@ RT_FLAG_COUNTERS = 1
 RT_FLAG_NO_SMEM = 2
 RT_FLAG_WIDE_BVH = 4
 RT_FLAG_BVH2 = 8
+RT_FLAG_LOCKSTEP = 16
 
 RT_COMM_ID_BYTES = 128
 
