@@ -107,8 +107,21 @@ def test_plane_hit_against_oracle():
     assert np.array_equal(np.isnan(want), np.isnan(got))
     hit = ~np.isnan(want)
     assert hit.sum() > 30_000
-    # numerator and denominator are FP64 on the device, the quotient FP32
-    assert (np.abs(got[hit] - want[hit]) / want[hit]).max() <= 1e-6
+    # Two evaluations on the device (rtfs_internal.h DUnbounded, classify_unbounded): planes with |n.p0| <= 16 take the
+    # FP32 expanded form k - n.o, the others the FP64 numerator and denominator; the quotient is FP32 in both.
+    k = (p * nrm).sum(1)
+    wide = hit & (np.abs(k) > 16.0)
+    assert wide.sum() > 20_000
+    assert (np.abs(got[wide] - want[wide]) / want[wide]).max() <= 1e-6
+    # FP32 class: k - n.o rounds at 6e-8 of |k| + |n.o| and n.d at 6e-8, so the bar of 1e-5 holds wherever the ray neither
+    # starts within 3 % of the plane (relative to those magnitudes) nor runs within 1e-2 of parallel to it; the filtered
+    # share is asserted small
+    near = hit & ~wide
+    height = np.abs(((p - o) * nrm).sum(1))
+    safe = near & (height > 3e-2 * (np.abs(k) + np.abs((o * nrm).sum(1)))) & (np.abs((d * nrm).sum(1)) > 1e-2)
+    assert near.sum() > 5_000 and safe.sum() > 0.9 * near.sum(), (near.sum(), safe.sum())
+    assert (np.abs(got[safe] - want[safe]) / want[safe]).max() <= REL
+    assert np.quantile(np.abs(got[near] - want[near]) / want[near], 0.99) <= REL
     # parallel ray and ray pointing away
     assert np.isnan(native.plane_hit([0, 1, 0], [1, 0, 0], [0, 0, 0], [0, 1, 0])[0])
     assert np.isnan(native.plane_hit([0, 1, 0], [0, 1, 0], [0, 0, 0], [0, 1, 0])[0])
