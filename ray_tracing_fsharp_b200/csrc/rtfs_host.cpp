@@ -758,6 +758,39 @@ int rt_scene_create(const RtHittable *objects, int32_t n_objects, const RtTextur
         if (x.kind != RT_TEX_COLOUR && !(std::fabs(x.map_radius) > 0.0))
             return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_create: texture " + std::to_string(t) + " has map_radius 0");
     }
+    // Checkered textures nest (Texture.fs:56-62); the device follows at most kMaxCheckerDepth levels, so deeper nests and
+    // cycles (which the reference's immutable values cannot even express) are refused here rather than rendered black
+    {
+        constexpr int kMaxCheckerDepth = 8;
+        std::vector<int> depth(size_t(n_textures), -1); // -1 unknown, -2 on the current path
+        std::vector<std::pair<int32_t, int>> stack;
+        for (int32_t root = 0; root < n_textures; ++root) {
+            if (depth[root] >= 0) continue;
+            stack.push_back({root, 0});
+            while (!stack.empty()) {
+                auto [t, phase] = stack.back();
+                const RtTexture &x = textures[t];
+                if (x.kind != RT_TEX_CHECKERED) {
+                    depth[t] = 0;
+                    stack.pop_back();
+                    continue;
+                }
+                if (phase == 0) {
+                    depth[t] = -2;
+                    stack.back().second = 1;
+                    for (int32_t c : {x.even, x.odd}) {
+                        if (depth[c] == -2) return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_create: checkered texture " + std::to_string(t) + " is part of a cycle");
+                        if (depth[c] == -1) stack.push_back({c, 0});
+                    }
+                } else {
+                    depth[t] = 1 + std::max(depth[x.even], depth[x.odd]);
+                    if (depth[t] > kMaxCheckerDepth)
+                        return fail(RT_ERR_UNSUPPORTED, "rt_scene_create: checkered textures nested deeper than " + std::to_string(kMaxCheckerDepth) + " levels");
+                    stack.pop_back();
+                }
+            }
+        }
+    }
     auto *s = new RtScene();
     s->objects.assign(objects, objects + n_objects);
     s->textures.assign(textures, textures + n_textures);

@@ -120,25 +120,32 @@ def f64(a, shape=None):
     return a.reshape(shape) if shape is not None else a
 
 
-_frame_buffers = {}
+class FrameRing:
+    """Explicit recycling of output frames, for a host that renders frame after frame: hands out `count` uint8 arrays of
+    one shape in turn (`next()`), each already touched.  Opt-in — pass `rgb_out=ring.next()` (or `frames=ring` to
+    Scene.render): the caller states that it is done with the frame it got `count` calls ago.  Without it every render
+    returns a fresh array that is never handed out again.  (A fresh np.empty is untouched memory, and the device->host copy
+    into it pays a page fault per 4 KiB — 1.3 ms for the 2.9 MB C2 frame; a .NET caller's zero-initialised, reused array
+    does not.)"""
+
+    def __init__(self, shape, count=2):
+        if count < 1:
+            raise ValueError("FrameRing needs at least one frame")
+        self.shape = tuple(shape)
+        self._frames = [np.zeros(self.shape, np.uint8) for _ in range(count)]
+        for f in self._frames:
+            f.fill(0)  # touch the pages now
+        self._at = 0
+
+    def next(self):
+        f = self._frames[self._at % len(self._frames)]
+        self._at += 1
+        return f
 
 
 def _frame_buffer(shape):
-    """An output frame for rt_render.  A previous frame of the same shape is handed out again once nobody holds it any
-    more (neither the array nor a view of it); up to three are kept per shape, so that a loop which still holds the
-    last frame while it renders the next one finds the one before.  A fresh np.empty is untouched memory, and the
-    device->host copy into it pays a page fault per 4 KiB (1.3 ms for the 2.9 MB C2 frame; a .NET caller's
-    zero-initialised array does not)."""
-    import sys
-    ring = _frame_buffers.setdefault(shape, [])
-    for i in range(len(ring)):
-        if sys.getrefcount(ring[i]) <= 2:  # the ring and getrefcount's argument
-            return ring[i]
-    buf = np.empty(shape, np.uint8)
-    if len(ring) >= 3:
-        ring.pop(0)
-    ring.append(buf)
-    return buf
+    """A fresh output frame (never recycled behind the caller's back; see FrameRing for the opt-in)."""
+    return np.empty(shape, np.uint8)
 
 
 def _as_array(ctype, items):

@@ -81,11 +81,12 @@ class Scene:
     @staticmethod
     def render(progress_increment: Callable[[float], None], print_fn: Callable[[str], None], max_width_coord: int, max_height_coord: int,
                camera: abi.RtCamera, s: "Scene", seed: Optional[int] = None, adaptive: bool = True, mode: int = abi.RT_MODE_MEGAKERNEL,
-               flags: int = 0):
+               flags: int = 0, frames: Optional["native.FrameRing"] = None):
         """Scene.render: returns (total progress, Image).  Like the reference it is lazy: nothing is
         traced until a row is forced; the first forced row renders the whole frame on the GPU.
         `seed`: key of the counter RNG; None draws one from the OS as `FloatProducer (Random ())` does
-        (Scene.fs:205).  `print_fn` is accepted and ignored exactly as the reference ignores it (Scene.fs:158)."""
+        (Scene.fs:205).  `frames`: a native.FrameRing to take the output array from (explicit reuse by a host that renders
+        frame after frame); by default every frame is a fresh array.  `print_fn` is accepted and ignored exactly as the reference ignores it (Scene.fs:158)."""
         rows, cols = 2 * max_height_coord + 1, 2 * max_width_coord + 1  # Scene.fs:208-209
         if seed is None:
             seed = secrets.randbits(64)
@@ -93,11 +94,13 @@ class Scene:
 
         def frame():
             if "rgb" not in state:
+                out = frames.next() if frames is not None else None
                 if isinstance(s._handle, native.MultiHandle):
-                    rgb, _, stats = s._handle.render(camera, max_width_coord, max_height_coord, seed=seed, adaptive=adaptive, flags=flags)
+                    rgb, _, stats = s._handle.render(camera, max_width_coord, max_height_coord, seed=seed, adaptive=adaptive, flags=flags,
+                                                     rgb_out=out)
                 else:
                     rgb, _, stats = s._handle.render(camera, max_width_coord, max_height_coord, seed=seed, adaptive=adaptive, mode=mode,
-                                                     flags=flags)
+                                                     flags=flags, rgb_out=out)
                 s.last_stats = stats
                 state["rgb"] = rgb
             return state["rgb"]

@@ -176,6 +176,25 @@ def test_scene_create_validates_like_the_type_system_would():
     assert create([ok], [t])[0] == abi.RT_ERR_UNSUPPORTED
     assert lib.rt_scene_create(None, 0, None, 0, -1, None) == abi.RT_ERR_INVALID_ARGUMENT
 
+    # checkered textures: cycles (A -> B -> A) and nests deeper than the device follows (8 levels) are refused
+    def checker(even, odd):
+        c = abi.RtTexture()
+        c.kind, c.even, c.odd, c.grid_size, c.map_radius = abi.RT_TEX_CHECKERED, even, odd, 4.0, 1.0
+        return c
+
+    def colour():
+        c = abi.RtTexture()
+        c.kind = abi.RT_TEX_COLOUR
+        return c
+
+    rc, msg = create([ok], [checker(1, 2), checker(0, 2), colour()])
+    assert rc == abi.RT_ERR_INVALID_ARGUMENT and "cycle" in msg
+    chain = [checker(i + 1, 9) for i in range(8)] + [colour(), colour()]  # 8 levels: the deepest the device follows
+    assert create([ok], chain)[0] == abi.RT_OK
+    chain = [checker(i + 1, 10) for i in range(9)] + [colour(), colour()]  # 9 levels
+    rc, msg = create([ok], chain)
+    assert rc == abi.RT_ERR_UNSUPPORTED and "nested deeper" in msg
+
 
 def test_closures_cannot_cross_the_abi():
     s = Hittable.Sphere(Sphere.make(SphereStyle.LambertReflection(1.0, Texture.Arbitrary(lambda p: Colour.Red)), (0, 0, 0), 1.0))
@@ -237,23 +256,19 @@ def test_reference_sample_scenes_marshal_and_render_on_the_oracle(name):
         assert (prim == 3).sum() > 1000 and not (prim == 4).any()
 
 
-def test_output_frames_are_recycled_only_when_nobody_holds_them():
-    """native._frame_buffer: rt_render's output array is handed out again only once neither it nor a view of it is
-    referenced (so no caller ever sees a frame change under its feet)."""
+def test_output_frames_are_never_recycled_unless_the_caller_opts_in():
+    """Every render gets a fresh output array by default (a caller holding only a raw pointer to an earlier frame must not
+    see it change); native.FrameRing is the explicit opt-in: `count` arrays handed out in turn."""
     shape = (7, 9, 3)
     a = native._frame_buffer(shape)
+    addr = a.ctypes.data
     b = native._frame_buffer(shape)
-    assert a is not b and a.shape == shape and a.dtype == np.uint8
-    row = a[2]          # a view keeps its base alive and unrecycled
-    ida = id(a)
-    del a
-    c = native._frame_buffer(shape)
-    assert id(c) != ida and c is not b
-    del row
-    d = native._frame_buffer(shape)
-    assert id(d) == ida  # released: recycled
-    held = [native._frame_buffer(shape) for _ in range(5)]  # more live frames than the ring keeps: all distinct
-    assert len({id(x) for x in held} | {id(b), id(c), id(d)}) == 8
+    assert a is not b and b.ctypes.data != addr and a.shape == shape and a.dtype == np.uint8
+    ring = native.FrameRing(shape, count=2)
+    f0, f1, f2 = ring.next(), ring.next(), ring.next()
+    assert f0 is not f1 and f2 is f0 and f0.shape == shape and f0.dtype == np.uint8
+    with pytest.raises(ValueError):
+        native.FrameRing(shape, count=0)
 
 
 def test_marshal_preserves_texture_structure():
