@@ -29,6 +29,8 @@ static void workspace_destroy(DeviceWorkspace *ws) {
     cudaFree(ws->d_list);
     cudaFree(ws->d_stats_b);
     cudaFree(ws->d_counters);
+    cudaFree(ws->d_blob);
+    if (ws->h_blob) cudaFreeHost(ws->h_blob);
     if (ws->h_counters) cudaFreeHost(ws->h_counters);
     for (auto &e : ws->ev)
         if (e) cudaEventDestroy(e);
@@ -135,8 +137,7 @@ void device_scene_free(RtScene *scene) {
     // device before the workspace and the texture arrays go back to pools another handle may draw from at once
     cudaDeviceSynchronize();
     cudaFree(ds->ref_nodes);
-    cudaFree(ds->blob);
-    cudaFree(ds->wide_blob);
+    cudaFree(ds->wide_blob); // (the main blob lives in the workspace)
     if (ds->ws) workspace_release(ds->ws);
     for (const PooledTexture &t : ds->images) texture_release(t);
     delete ds;
@@ -201,17 +202,31 @@ int device_scene_upload(RtScene *scene) {
     const size_t off_ref = align(off_unb + L.unbounded.size() * sizeof(DUnbounded));
     const size_t off_tex = off_ref;
     const size_t total = align(off_tex + dt.size() * sizeof(DTexture)) + 256;
-    std::vector<uint8_t> host(total, 0);
+    DeviceWorkspace *ws = ds->ws;
+    if (ws->blob_cap < total) { // grow the pooled blob and its pinned staging copy
+        cudaFree(ws->d_blob);
+        if (ws->h_blob) cudaFreeHost(ws->h_blob);
+        ws->d_blob = ws->h_blob = nullptr;
+        ws->blob_cap = 0;
+        const size_t cap = std::max<size_t>(total + total / 2, 256 << 10);
+        if (cudaMalloc(&ws->d_blob, cap) != cudaSuccess || cudaMallocHost(&ws->h_blob, cap) != cudaSuccess) {
+            cudaFree(ws->d_blob);
+            ws->d_blob = nullptr;
+            return bail(fail(RT_ERR_CUDA, "cudaMalloc failed for the scene"));
+        }
+        ws->blob_cap = cap;
+    }
+    uint8_t *host = static_cast<uint8_t *>(ws->h_blob);
     auto put = [&](size_t off, const void *src, size_t n) {
-        if (n) std::memcpy(host.data() + off, src, n);
+        if (n) std::memcpy(host + off, src, n);
     };
     put(off_nodes, L.nodes.data(), L.nodes.size() * sizeof(DNode));
     put(off_spheres, L.spheres.data(), L.spheres.size() * sizeof(DSphere));
     put(off_mats, L.materials.data(), L.materials.size() * sizeof(DMaterial));
     put(off_unb, L.unbounded.data(), L.unbounded.size() * sizeof(DUnbounded));
     put(off_tex, dt.data(), dt.size() * sizeof(DTexture));
-    if (cudaMalloc(&ds->blob, total) != cudaSuccess) return bail(fail(RT_ERR_CUDA, "cudaMalloc failed for the scene"));
-    if (cudaMemcpy(ds->blob, host.data(), total, cudaMemcpyHostToDevice) != cudaSuccess)
+    ds->blob = ws->d_blob;
+    if (cudaMemcpyAsync(ds->blob, host, total, cudaMemcpyHostToDevice, ws->stream) != cudaSuccess || cudaStreamSynchronize(ws->stream) != cudaSuccess)
         return bail(fail(RT_ERR_CUDA, "host->device copy of the scene failed"));
     ds->bytes += total;
     uint8_t *base = static_cast<uint8_t *>(ds->blob);

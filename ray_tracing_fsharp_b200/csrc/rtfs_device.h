@@ -51,6 +51,11 @@ struct DeviceWorkspace {
     uint8_t *d_rgb = nullptr;
     size_t list_pixels = 0; // flagged-pixel list of the main phase
     uint32_t *d_list = nullptr;
+    // the scene blob of the handle that holds this workspace, and its pinned staging copy: pooled with the workspace so
+    // that creating a scene costs one copy, not a cudaMalloc / cudaFree pair (grow-only)
+    void *d_blob = nullptr;
+    void *h_blob = nullptr;
+    size_t blob_cap = 0;
     unsigned long long *d_counters = nullptr;
     unsigned long long *h_counters = nullptr; // pinned
     cudaStream_t stream = nullptr;
@@ -69,7 +74,7 @@ struct DeviceScene {
     SceneGlobal g{};
     DRefNode *ref_nodes = nullptr;
     int32_t n_ref_nodes = 0;
-    void *blob = nullptr; // one allocation holding nodes | spheres | materials | unbounded | reference nodes | textures
+    void *blob = nullptr; // nodes | spheres | materials | unbounded | textures, in the workspace's pooled allocation (not owned)
     void *wide_blob = nullptr; // the 8-wide compressed tree: nodes | spheres in its order | the two index maps
     int32_t wide_depth = 0;
     std::vector<PooledTexture> images; // image textures borrowed from the pool

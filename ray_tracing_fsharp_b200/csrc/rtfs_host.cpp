@@ -194,43 +194,64 @@ struct SahBuilder {
     int split(int lo, int hi, int depth) {
         int n = hi - lo;
         int mid = -1;
+        FBox cb;
+        cb.reset();
+        for (int i = lo; i < hi; ++i) cb.grow(prims[i].c, prims[i].c);
         if (n > 2 && depth < 40) {
-            FBox cb;
-            cb.reset();
-            for (int i = lo; i < hi; ++i) cb.grow(prims[i].c, prims[i].c);
             constexpr int BINS = 16;
+            // one pass over the primitives fills the bins of all three axes
+            FBox bb[3][BINS];
+            int cnt[3][BINS];
+            float scale[3];
+            bool live[3];
+            for (int axis = 0; axis < 3; ++axis) {
+                float ext = cb.mx[axis] - cb.mn[axis];
+                live[axis] = ext > 0.f;
+                scale[axis] = live[axis] ? float(BINS) / ext : 0.f;
+                for (int k = 0; k < BINS; ++k) {
+                    bb[axis][k].reset();
+                    cnt[axis][k] = 0;
+                }
+            }
+            for (int i = lo; i < hi; ++i) {
+                const BuildPrim &p = prims[i];
+                for (int axis = 0; axis < 3; ++axis) {
+                    if (!live[axis]) continue;
+                    int k = std::min(BINS - 1, std::max(0, int((p.c[axis] - cb.mn[axis]) * scale[axis])));
+                    bb[axis][k].grow(p.mn, p.mx);
+                    cnt[axis][k]++;
+                }
+            }
             double best = std::numeric_limits<double>::infinity();
             int best_axis = -1, best_bin = -1;
             for (int axis = 0; axis < 3; ++axis) {
-                float ext = cb.mx[axis] - cb.mn[axis];
-                if (!(ext > 0.f)) continue;
-                FBox bb[BINS];
-                int cnt[BINS] = {0};
-                for (auto &b : bb) b.reset();
-                float scale = float(BINS) / ext;
-                for (int i = lo; i < hi; ++i) {
-                    int k = std::min(BINS - 1, std::max(0, int((prims[i].c[axis] - cb.mn[axis]) * scale)));
-                    bb[k].grow(prims[i].mn, prims[i].mx);
-                    cnt[k]++;
-                }
+                if (!live[axis]) continue;
                 double right_area[BINS];
                 int right_cnt[BINS];
                 FBox acc;
                 acc.reset();
                 int c = 0;
+                double area = 0.0; // of `acc`: recomputed only when a bin adds something (most bins of a small node are empty)
                 for (int k = BINS - 1; k > 0; --k) {
-                    if (cnt[k]) acc.grow(bb[k].mn, bb[k].mx);
-                    c += cnt[k];
-                    right_area[k] = acc.area();
+                    if (cnt[axis][k]) {
+                        acc.grow(bb[axis][k].mn, bb[axis][k].mx);
+                        area = acc.area();
+                    }
+                    c += cnt[axis][k];
+                    right_area[k] = area;
                     right_cnt[k] = c;
                 }
                 acc.reset();
                 c = 0;
+                area = 0.0;
                 for (int k = 0; k < BINS - 1; ++k) {
-                    if (cnt[k]) acc.grow(bb[k].mn, bb[k].mx);
-                    c += cnt[k];
+                    if (cnt[axis][k]) {
+                        acc.grow(bb[axis][k].mn, bb[axis][k].mx);
+                        area = acc.area();
+                    }
+                    c += cnt[axis][k];
                     if (c == 0 || right_cnt[k + 1] == 0) continue;
-                    double cost = acc.area() * c + right_area[k + 1] * right_cnt[k + 1];
+                    double cost = area * c + right_area[k + 1] * right_cnt[k + 1];
                     if (cost < best) {
                         best = cost;
                         best_axis = axis;
@@ -239,19 +260,15 @@ struct SahBuilder {
                 }
             }
             if (best_axis >= 0) {
-                float ext = cb.mx[best_axis] - cb.mn[best_axis];
-                float scale = float(BINS) / ext;
+                const float sc = scale[best_axis], c0 = cb.mn[best_axis];
                 auto it = std::partition(prims.begin() + lo, prims.begin() + hi, [&](const BuildPrim &p) {
-                    int k = std::min(BINS - 1, std::max(0, int((p.c[best_axis] - cb.mn[best_axis]) * scale)));
+                    int k = std::min(BINS - 1, std::max(0, int((p.c[best_axis] - c0) * sc)));
                     return k <= best_bin;
                 });
                 mid = int(it - prims.begin());
             }
         }
         if (mid <= lo || mid >= hi) { // median split on the widest centroid axis
-            FBox cb;
-            cb.reset();
-            for (int i = lo; i < hi; ++i) cb.grow(prims[i].c, prims[i].c);
             int axis = 0;
             for (int a = 1; a < 3; ++a)
                 if (cb.mx[a] - cb.mn[a] > cb.mx[axis] - cb.mn[axis]) axis = a;
@@ -425,13 +442,27 @@ void build_device_layout(const RtHittable *objs, int32_t n_objs, HostSceneLayout
         L.materials.push_back(make_material(h, i));
     }
     L.device_id_of = device_id_of; // bounded spheres with negative radius keep id -1: they can never be returned
-    if (n >= 1) {
-        FBox rootb = b.bounds(0, n);
-        if (n == 1) {
-            export_sah(L, b.leaf_obj, L.nodes[0].left, rootb.mn, rootb.mx, sah_tree_out);
-        } else {
-            export_sah(L, b.leaf_obj, 0, rootb.mn, rootb.mx, sah_tree_out);
-        }
+    (void)sah_tree_out; // the inspection form of the tree is made on first request (scene_ensure_sah_tree)
+}
+
+// The SAH tree in the HostNode form rt_scene_bvh_nodes hands out: only inspection asks for it, so it is built on first use.
+void scene_ensure_sah_tree(RtScene *s) {
+    if (s->sah_built) return;
+    s->sah_built = true;
+    const HostSceneLayout &L = s->layout;
+    s->sah_tree.clear();
+    if (L.n_bounded < 1) return;
+    std::vector<int32_t> leaf_obj(size_t(L.n_bounded));
+    for (int32_t k = 0; k < L.n_bounded; ++k) leaf_obj[k] = L.materials[k].host_index;
+    FBox rootb;
+    rootb.reset();
+    if (L.root_is_leaf) {
+        rootb.grow(L.nodes[0].l_mn, L.nodes[0].l_mx);
+        export_sah(L, leaf_obj, L.nodes[0].left, rootb.mn, rootb.mx, s->sah_tree);
+    } else {
+        rootb.grow(L.nodes[0].l_mn, L.nodes[0].l_mx);
+        rootb.grow(L.nodes[0].r_mn, L.nodes[0].r_mx);
+        export_sah(L, leaf_obj, 0, rootb.mn, rootb.mx, s->sah_tree);
     }
 }
 
@@ -830,11 +861,13 @@ void rt_scene_destroy(RtScene *scene) {
 int rt_scene_bvh_node_count(const RtScene *scene, int32_t which) {
     if (!scene) return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_bvh_node_count: null scene");
     if (which == RT_BVH_REFERENCE) scene_ensure_reference(const_cast<RtScene *>(scene));
+    else scene_ensure_sah_tree(const_cast<RtScene *>(scene));
     return int(which == RT_BVH_REFERENCE ? scene->ref_tree.size() : scene->sah_tree.size());
 }
 int rt_scene_bvh_nodes(const RtScene *scene, int32_t which, double *bounds, int32_t *right, int32_t *prim) {
     if (!scene || !bounds || !right || !prim) return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_bvh_nodes: null argument");
     if (which == RT_BVH_REFERENCE) scene_ensure_reference(const_cast<RtScene *>(scene));
+    else scene_ensure_sah_tree(const_cast<RtScene *>(scene));
     const auto &t = which == RT_BVH_REFERENCE ? scene->ref_tree : scene->sah_tree;
     for (size_t i = 0; i < t.size(); ++i) {
         for (int a = 0; a < 3; ++a) {

@@ -156,6 +156,7 @@ struct RtScene {
     std::vector<std::vector<uint8_t>> texture_pixels;
     std::vector<rtfs::HostNode> ref_tree, sah_tree;
     bool ref_built = false; // the reference-topology tree is built on first use (scene_ensure_reference)
+    bool sah_built = false; // likewise the inspection form of the SAH tree (scene_ensure_sah_tree)
     rtfs::HostSceneLayout layout;
     int32_t device = -1;
     void *dev = nullptr; // rtfs_device.cu: DeviceScene*
@@ -164,6 +165,7 @@ struct RtScene {
 // implemented in rtfs_device.cu
 namespace rtfs {
 void scene_ensure_reference(RtScene *scene);
+void scene_ensure_sah_tree(RtScene *scene);
 int device_scene_upload(RtScene *scene);
 int device_scene_ensure_reference(RtScene *scene);
 int device_scene_ensure_wide(RtScene *scene);
