@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -529,7 +530,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) render_kernel(const FramePar
 // RING of 64 rays in shared memory.  A ray is READY (waiting for its walk), WALKING (one per lane, its walk state in that
 // lane's registers and stack), WALKED (closest sphere known, waiting for the rest of hitObject and for its scatter) or
 // the slot is EMPTY.  The warp alternates:
-//   * walk quanta: every lane that has a ray performs up to kFlowQuantum node visits; lanes whose walk ended hand the
+//   * walk quanta: every lane that has a ray performs up to `quantum` node visits; lanes whose walk ended hand the
 //     result to the ring and take the next READY ray at the next schedule point, so a long walk delays nobody;
 //   * a shading pass as soon as 32 rays are WALKED: unbounded objects, strike point, scatter, bounce count
 //     (Scene.fs:77-114) for 32 rays at full width; a path that ends is accumulated into its item (PixelStats.add) and its
@@ -540,7 +541,10 @@ __global__ void __launch_bounds__(kBlockThreads, 1) render_kernel(const FramePar
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kRing = 64;          // ray slots per warp
 constexpr int kFlowItems = 3;      // work items a warp can have in flight
-constexpr int kFlowQuantum = 4;    // node visits between two schedule points
+// node visits between two schedule points (FrameParams.quantum): a lane whose walk ends waits for the next schedule point
+// to take another ray, and a schedule point costs ~50 issue slots when some lane does; 4 suits walks of ~13 visits (the RTOW
+// scene), 8 walks of ~34 (the 100 k-sphere scene).  RTFS_FLOW_QUANTUM overrides both (tuning runs).
+constexpr int kFlowQuantumSmall = 4, kFlowQuantumBig = 8;
 constexpr int kMaxFlowDepth = 253; // the bounce count shares a word with the colour
 enum RingField { RF_OX = 0, RF_OY, RF_OZ, RF_DX, RF_DY, RF_DZ, RF_COLOUR, RF_LAST, RF_WHERE, RF_T, RF_REF, RF_FIELDS };
 struct FlowItem {
@@ -817,7 +821,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) render_flow_kernel(const Fra
             if (walking == 0u) break; // nothing walking, nothing READY, nothing WALKED: the warp's work is done
             // ---- a quantum of the walk ----
 #pragma unroll 1
-            for (int v = 0; v < kFlowQuantum; ++v) {
+            for (int v = 0; v < fp.quantum; ++v) {
                 if (have && !done) done = bvh_visit<SMEM, COUNT>(sc, rs, o, d, last, node, sp, stack, best_t, best, cn);
             }
             // ---- finished walks go to the ring ----
@@ -962,6 +966,13 @@ static int plan_launch(DeviceScene *ds, FrameParams &fp, bool probe, bool count,
     const size_t stack_q = size_t(wide ? 2 * (ds->wide_depth + 1) : ds->max_depth + 1) * kBlockThreads * 4 / 16;
     const bool sstack = !flow && !smem && ds->g.n_bounded > 0 && (used_q + stack_q) * 16 + 1024 <= ds->ws->smem_optin;
     fp.s_stack = uint32_t(used_q);
+    {
+        static const int forced = [] {
+            const char *e = std::getenv("RTFS_FLOW_QUANTUM");
+            return e ? std::max(1, std::min(64, std::atoi(e))) : 0;
+        }();
+        fp.quantum = forced ? forced : (smem ? kFlowQuantumSmall : kFlowQuantumBig);
+    }
     fp.stack_levels = int32_t(stack_q * 16 / (kBlockThreads * 4));
     plan.smem_bytes = (used_q + (sstack ? stack_q : 0)) * 16;
     fn = flow ? (probe ? pick_flow<true>(smem, count) : pick_flow<false>(smem, count)) : pick_kernel(probe, smem, count, sstack, wide);

@@ -114,6 +114,7 @@ struct FrameParams {
     uint32_t s_stack; // SSTACK kernels: the walk stacks, one column of `stack_levels` words per thread (uint4 units)
     int32_t opt_flags; // RtRenderOpts.flags
     int32_t stack_levels; // words per thread of the shared-memory walk stacks
+    int32_t quantum;      // flow kernel: node visits between two schedule points
 };
 
 
