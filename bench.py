@@ -395,7 +395,7 @@ def run_ours(args):
     r = Runner(args)
     torch, rank, world = r.torch, r.rank, r.world
     r.flags = ((abi.RT_FLAG_NO_SMEM if args.no_smem else 0) | {"auto": 0, "binary": abi.RT_FLAG_BVH2, "wide": abi.RT_FLAG_WIDE_BVH}[args.bvh]
-               | (abi.RT_FLAG_LOCKSTEP if args.schedule == "lockstep" else 0))
+               | (abi.RT_FLAG_FLOW if args.schedule == "flow" else 0))
     spec = build_spec(args)
     handle, cam = r.scene(spec)
     fp32_peak = native.measure_fp32_peak(r.local_rank) if rank == 0 else 0.0
@@ -538,9 +538,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--bvh", default="auto", choices=["auto", "binary", "wide"],
                     help="which tree the kernels walk: auto = binary in shared memory when the scene fits, else 8-wide compressed (A/B runs)")
-    ap.add_argument("--schedule", default="flow", choices=["flow", "lockstep"],
-                    help="flow = a ring of 64 rays per warp, walks pulled by the lanes, scatters in full-width passes (default); "
-                         "lockstep = one ray per lane per pass (round 1's kernel, for A/B runs)")
+    ap.add_argument("--schedule", default="lockstep", choices=["flow", "lockstep"],
+                    help="lockstep = one ray per lane per pass (default); flow = a ring of 64 rays per warp, walks pulled by the "
+                         "lanes, scatters in full-width passes (measured slower; for A/B runs)")
     ap.add_argument("--no-hash", action="store_true", help="skip the fixed-seed frame hashed through every product path")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the short measurements of the other BASELINE configs")
     ap.add_argument("--other-configs", default="C1,C3,C4,native,C5", help="which of C1..C5 / native to measure after the headline config")

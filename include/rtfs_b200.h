@@ -132,8 +132,10 @@ typedef struct RtRenderOpts {
 #define RT_FLAG_WIDE_BVH 4 /* walk the 8-wide compressed tree (read from global memory) instead of the binary one:
                               measured slower on B200 for every scene tried, kept selectable          */
 #define RT_FLAG_BVH2 8     /* walk the binary tree (the default; overrides RT_FLAG_WIDE_BVH)                      */
-#define RT_FLAG_LOCKSTEP 16 /* the round-1 schedule: the 32 lanes of a warp trace one ray each per pass, in lockstep,
-                              instead of pulling walks from a ring of 64 rays per warp (A/B comparisons)          */
+#define RT_FLAG_LOCKSTEP 16 /* the default schedule, spelt out: the 32 lanes of a warp trace one ray each per pass      */
+#define RT_FLAG_FLOW 32     /* the flow schedule: every warp keeps a ring of 64 rays in shared memory, lanes pull walks
+                              from it in quanta, scatters run in full-width passes.  Bit-identical frames; measured
+                              slower than lockstep on B200, kept selectable                          */
 
 typedef struct RtStats {
     uint64_t paths;     /* traceOnce calls (Scene.fs:118)                                        */

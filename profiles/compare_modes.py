@@ -15,7 +15,8 @@ from ray_tracing_fsharp_b200.scene import Camera  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--config", default="C2")
 ap.add_argument("--spp", type=int, default=0)
-ap.add_argument("--modes", default="megakernel,wavefront")
+ap.add_argument("--modes", default="megakernel,wavefront", help="comma-separated: megakernel (the default lockstep schedule), flow, wide, wavefront")
+ap.add_argument("--quantum", default="")
 ap.add_argument("--repeat", type=int, default=1)
 args = ap.parse_args()
 spec = sample_images.CONFIGS[args.config]()
@@ -27,7 +28,8 @@ hs, ts, keep = marshal(spec.objects)
 scene = native.SceneHandle(hs, ts, 0, keepalive=keep)
 for mode in args.modes.split(","):
     m = abi.RT_MODE_WAVEFRONT if mode == "wavefront" else abi.RT_MODE_MEGAKERNEL
+    flags = {"flow": abi.RT_FLAG_FLOW, "wide": abi.RT_FLAG_WIDE_BVH}.get(mode, 0)
     for _ in range(args.repeat):
-        rgb, _, st = scene.render(cam, spec.max_width_coord, spec.max_height_coord, seed=5, mode=m)
+        rgb, _, st = scene.render(cam, spec.max_width_coord, spec.max_height_coord, seed=5, mode=m, flags=flags)
         print(f"{mode:10s} {spec.cols}x{spec.rows} {spec.spp}spp: kernels {st.kernel_ms:9.2f} ms  total {st.total_ms:9.2f} ms  launches {st.launches:5d}  "
               f"paths {st.paths}  rays {st.rays}  => {st.rays / st.kernel_ms / 1e3:9.1f} Mrays/s", flush=True)

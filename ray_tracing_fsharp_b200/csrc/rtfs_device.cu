@@ -944,9 +944,9 @@ static RenderKernelFn pick_kernel(bool probe, bool smem, bool count, bool sstack
 // lays out shared memory and sizes the persistent grid
 static int plan_launch(DeviceScene *ds, FrameParams &fp, bool probe, bool count, bool no_smem, LaunchPlan &plan, RenderKernelFn &fn) {
     const bool wide_asked = frame_walks_wide_tree(ds, fp.opt_flags, true);
-    // the flow schedule (ring of rays per warp) unless the lockstep one is asked for, the wide tree is (it has no flow
-    // variant), or the bounce budget does not fit the byte it shares with the colour
-    const bool flow = !(fp.opt_flags & RT_FLAG_LOCKSTEP) && !wide_asked && fp.cam.depth <= kMaxFlowDepth;
+    // the flow schedule (ring of rays per warp) on request only — measured slower than lockstep on B200 —
+    // and not with the wide tree (no flow variant) nor when the bounce budget does not fit the byte it shares with the colour
+    const bool flow = (fp.opt_flags & RT_FLAG_FLOW) && !(fp.opt_flags & RT_FLAG_LOCKSTEP) && !wide_asked && fp.cam.depth <= kMaxFlowDepth;
     const size_t warp_q = (kBlockThreads / 32) * (flow ? sizeof(FlowWarp) : sizeof(WarpScratch)) / 16;
     const size_t nodes_q = size_t(ds->g.n_nodes) * 4, sph_q = size_t(ds->g.n_bounded), mat_q = size_t(ds->g.n_bounded + ds->g.n_unbounded) * 2;
     const size_t scene_q = nodes_q + sph_q + mat_q;
@@ -1162,7 +1162,7 @@ int rt_device_count(void) {
 size_t rt_scene_shared_memory_bytes(const RtScene *scene) {
     if (!scene || !scene->dev) return 0;
     auto *ds = static_cast<const DeviceScene *>(scene->dev);
-    const size_t warp_q = (kBlockThreads / 32) * sizeof(FlowWarp) / 16; // the default (flow) schedule's per-warp scratch
+    const size_t warp_q = (kBlockThreads / 32) * sizeof(WarpScratch) / 16; // the default (lockstep) schedule's per-warp scratch
     const size_t scene_q = size_t(ds->g.n_nodes) * 4 + size_t(ds->g.n_bounded) + size_t(ds->g.n_bounded + ds->g.n_unbounded) * 2;
     bool smem = (scene_q + warp_q) * 16 + 1024 <= ds->ws->smem_optin && ds->g.n_bounded > 0;
     return smem ? scene_q * 16 : 0;

@@ -166,8 +166,8 @@ def test_wide_bvh_and_binary_bvh_agree_bit_for_bit(which):
 
 @pytest.mark.parametrize("which", ["reduced", "C1", "C2", "C3", "C4", "mid", "empty-ish"])
 def test_flow_and_lockstep_schedules_agree_bit_for_bit(which):
-    """The default schedule (render_flow_kernel: a ring of 64 rays per warp, walks pulled by the lanes, scatters done in
-    full-width passes) against round 1's lockstep kernel (RT_FLAG_LOCKSTEP): same RNG keys, same integer sums, so the
+    """The flow schedule (RT_FLAG_FLOW, render_flow_kernel: a ring of 64 rays per warp, walks pulled by the lanes, scatters
+    done in full-width passes) against the default lockstep kernel: same RNG keys, same integer sums, so the
     accumulators, the path / ray counts and the early-out decisions must be identical — scene in shared memory, scene in
     global memory, with the counters on, adaptive and not, probe-only frames, and a frame smaller than one warp's ring."""
     if which == "reduced":
@@ -182,9 +182,9 @@ def test_flow_and_lockstep_schedules_agree_bit_for_bit(which):
     mw, mh = spec.max_width_coord, spec.max_height_coord
     for adaptive in (True, False):
         for extra in (0, abi.RT_FLAG_NO_SMEM, abi.RT_FLAG_COUNTERS):
-            a, sa, sta = dsc.render(cam, mw, mh, seed=47, adaptive=adaptive, want_sums=True, flags=extra | abi.RT_FLAG_LOCKSTEP)
+            a, sa, sta = dsc.render(cam, mw, mh, seed=47, adaptive=adaptive, want_sums=True, flags=extra)
             sa = sa.copy()
-            b, sb, stb = dsc.render(cam, mw, mh, seed=47, adaptive=adaptive, want_sums=True, flags=extra)
+            b, sb, stb = dsc.render(cam, mw, mh, seed=47, adaptive=adaptive, want_sums=True, flags=extra | abi.RT_FLAG_FLOW)
             assert np.array_equal(sa, sb), (which, adaptive, extra, int((sa != sb).any(2).sum()))
             assert int(sta.rays) == int(stb.rays) and int(sta.paths) == int(stb.paths)
             assert int(sta.pixels_early_out) == int(stb.pixels_early_out)
@@ -193,9 +193,9 @@ def test_flow_and_lockstep_schedules_agree_bit_for_bit(which):
     # spp values that exercise the chunk table's tail (1-sample items) and a probe-only frame
     for spp in (1, 5, 11, 12, 33):
         cam.samples_per_pixel = spp
-        _, s1, _ = dsc.render(cam, mw, mh, seed=48, adaptive=True, want_sums=True, flags=abi.RT_FLAG_LOCKSTEP)
+        _, s1, _ = dsc.render(cam, mw, mh, seed=48, adaptive=True, want_sums=True)
         s1 = s1.copy()
-        _, s2, _ = dsc.render(cam, mw, mh, seed=48, adaptive=True, want_sums=True)
+        _, s2, _ = dsc.render(cam, mw, mh, seed=48, adaptive=True, want_sums=True, flags=abi.RT_FLAG_FLOW)
         assert np.array_equal(s1, s2), (which, spp)
 
 
