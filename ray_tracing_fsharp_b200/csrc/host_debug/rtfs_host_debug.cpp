@@ -98,7 +98,9 @@ int build(HostScene &hs, const RtHittable *objects, int n_objects, const RtTextu
         hs.texels[i] = HostTexels{t.rgb8, t.width, t.height};
         o.tex = reinterpret_cast<unsigned long long>(&hs.texels[i]);
     }
-    hs.nodes = exact_copy<uint4>(L.nodes);
+    std::vector<DNode> dev_nodes(L.nodes.size());
+    for (size_t i = 0; i < L.nodes.size(); ++i) dev_nodes[i] = device_node_of(L.nodes[i]); // what device_scene_upload does
+    hs.nodes = exact_copy<uint4>(dev_nodes);
     hs.spheres = exact_copy<float4>(L.spheres);
     hs.mats = exact_copy<uint4>(L.materials);
     hs.unb.reset(new DUnbounded[L.unbounded.size()]);

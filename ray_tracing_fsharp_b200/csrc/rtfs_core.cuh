@@ -233,9 +233,9 @@ RTFS_HD bool aabb_hits_ref(float3 inv, float3 o, const float mn[3], const float 
 RTFS_HD float3 inverse_directions(float3 d) { return f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z); }
 
 // Slab test of the render traversal.  Per ray: inv = 1 / d (components clamped away from zero, so no
-// 0 * inf = NaN arises), noi = -o * inv, and pad = an absolute bound on the rounding of mn * inv + noi; per box:
-// six FFMAs.  Conservative: boxes are rounded outwards on the host, t_far is padded by 3 ulp (Ize, "Robust BVH
-// Ray Traversal") plus `pad`.  Returns the entry distance for ordering and culls against the best hit so far
+// 0 * inf = NaN arises), noi = -o * inv, and pad = an absolute bound on the rounding of c * inv + noi; per box:
+// twelve FMA-pipe operations and five min / max / compare (see slab_entry).  Conservative: boxes are rounded outwards on
+// the host, t_far is padded by 5 ulp (Ize, "Robust BVH Ray Traversal") plus `pad`.  Returns the entry distance for ordering and culls against the best hit so far
 // (a finite number: kNoHitT while nothing is hit, so that the box {+inf, +inf} of a one-leaf tree is never
 // entered).  It may accept a box the reference rejects only for rays within rounding of a box face; closest-hit
 // results do not depend on it (rt_test_hit_object(traversal = 0) checks them against the oracle).
@@ -252,15 +252,18 @@ RTFS_HD RaySlabs make_slabs(float3 o, float3 d) {
     // approximate reciprocals (1 ulp): the slab test is padded, and noi is built from the same inv
     r.inv = f3(rcp_fast(x), rcp_fast(y), rcp_fast(z)); // |x|, |y|, |z| >= 1e-30: normal numbers
     r.noi = f3(-o.x * r.inv.x, -o.y * r.inv.y, -o.z * r.inv.z);
-    r.pad = 4.8e-7f * fmaxf(fmaxf(fabsf(r.noi.x), fabsf(r.noi.y)), fabsf(r.noi.z));
+    r.pad = 7.2e-7f * fmaxf(fmaxf(fabsf(r.noi.x), fabsf(r.noi.y)), fabsf(r.noi.z));
     return r;
 }
-RTFS_HD bool slab_entry(const RaySlabs &r, float mnx, float mny, float mnz, float mxx, float mxy, float mxz, float best_t, float &entry) {
-    float ax = fmaf(mnx, r.inv.x, r.noi.x), bx = fmaf(mxx, r.inv.x, r.noi.x);
-    float ay = fmaf(mny, r.inv.y, r.noi.y), by = fmaf(mxy, r.inv.y, r.noi.y);
-    float az = fmaf(mnz, r.inv.z, r.noi.z), bz = fmaf(mxz, r.inv.z, r.noi.z);
-    float t_near = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
-    float t_far = fmaf(fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)), 1.0000003576278687f, r.pad);
+// The box comes as centre c and half-extent h >= 0 (rtfs_internal.h, device_node_of): per axis the two plane distances are
+// t_c -+ |h inv| with t_c = c inv + noi, so near and far need no min / max pair (FMNMX, ALU pipe) — an FFMA, an FMUL and two
+// FADDs with an |x| operand, all on the FMA pipe.  Three roundings per distance instead of one: t_far is padded by 5 ulp + pad.
+RTFS_HD bool slab_entry(const RaySlabs &r, float cx, float cy, float cz, float hx, float hy, float hz, float best_t, float &entry) {
+    const float tx = fmaf(cx, r.inv.x, r.noi.x), ux = fabsf(hx * r.inv.x);
+    const float ty = fmaf(cy, r.inv.y, r.noi.y), uy = fabsf(hy * r.inv.y);
+    const float tz = fmaf(cz, r.inv.z, r.noi.z), uz = fabsf(hz * r.inv.z);
+    float t_near = fmaxf(fmaxf(tx - ux, ty - uy), fmaxf(tz - uz, 0.0f));
+    float t_far = fmaf(fminf(fminf(tx + ux, ty + uy), tz + uz), 1.0000005960464478f, r.pad);
     entry = t_near;
     return t_near <= fminf(t_far, best_t);
 }

@@ -221,7 +221,10 @@ int device_scene_upload(RtScene *scene) {
     auto put = [&](size_t off, const void *src, size_t n) {
         if (n) std::memcpy(host + off, src, n);
     };
-    put(off_nodes, L.nodes.data(), L.nodes.size() * sizeof(DNode));
+    { // the device walks centre / half-extent boxes (rtfs_internal.h)
+        DNode *dn = reinterpret_cast<DNode *>(host + off_nodes);
+        for (size_t i = 0; i < L.nodes.size(); ++i) dn[i] = device_node_of(L.nodes[i]);
+    }
     put(off_spheres, L.spheres.data(), L.spheres.size() * sizeof(DSphere));
     put(off_mats, L.materials.data(), L.materials.size() * sizeof(DMaterial));
     put(off_unb, L.unbounded.data(), L.unbounded.size() * sizeof(DUnbounded));

@@ -430,6 +430,28 @@ void classify_unbounded(DUnbounded &u) {
     }
 }
 
+// min / max boxes -> centre / half-extent boxes (see rtfs_internal.h), never smaller than the original
+DNode device_node_of(const DNode &n) {
+    DNode d = n;
+    auto conv = [](const float *mn, const float *mx, float *c_out, float *h_out) {
+        for (int a = 0; a < 3; ++a) {
+            if (!std::isfinite(mn[a]) || !std::isfinite(mx[a])) { // the never-entered dummy box of a one-sphere tree
+                c_out[a] = 1e30f;
+                h_out[a] = 0.f;
+                continue;
+            }
+            float c = float(0.5 * (double(mn[a]) + double(mx[a])));
+            double h = std::max(double(mx[a]) - double(c), double(c) - double(mn[a]));
+            float hf = round_up(h);
+            c_out[a] = c;
+            h_out[a] = std::nextafterf(hf, std::numeric_limits<float>::infinity());
+        }
+    };
+    conv(n.l_mn, n.l_mx, d.l_mn, d.l_mx); // l_mn now holds the centre, l_mx the half-extent
+    conv(n.r_mn, n.r_mx, d.r_mn, d.r_mx);
+    return d;
+}
+
 void build_device_layout(const RtHittable *objs, int32_t n_objs, HostSceneLayout &L, std::vector<HostNode> &sah_tree_out) {
     L = HostSceneLayout{};
     sah_tree_out.clear();
