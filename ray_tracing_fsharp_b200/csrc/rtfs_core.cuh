@@ -240,7 +240,7 @@ RTFS_HD float3 inverse_directions(float3 d) { return f3(1.0f / d.x, 1.0f / d.y, 
 // entered).  It may accept a box the reference rejects only for rays within rounding of a box face; closest-hit
 // results do not depend on it (rt_test_hit_object(traversal = 0) checks them against the oracle).
 struct RaySlabs {
-    float3 inv, noi;
+    float3 inv, noi, ainv; // 1 / d, -o / d, |1 / d|
     float pad;
 };
 RTFS_HD RaySlabs make_slabs(float3 o, float3 d) {
@@ -252,6 +252,7 @@ RTFS_HD RaySlabs make_slabs(float3 o, float3 d) {
     // approximate reciprocals (1 ulp): the slab test is padded, and noi is built from the same inv
     r.inv = f3(rcp_fast(x), rcp_fast(y), rcp_fast(z)); // |x|, |y|, |z| >= 1e-30: normal numbers
     r.noi = f3(-o.x * r.inv.x, -o.y * r.inv.y, -o.z * r.inv.z);
+    r.ainv = f3(fabsf(r.inv.x), fabsf(r.inv.y), fabsf(r.inv.z));
     r.pad = 7.2e-7f * fmaxf(fmaxf(fabsf(r.noi.x), fabsf(r.noi.y)), fabsf(r.noi.z));
     return r;
 }
@@ -259,11 +260,9 @@ RTFS_HD RaySlabs make_slabs(float3 o, float3 d) {
 // t_c -+ |h inv| with t_c = c inv + noi, so near and far need no min / max pair (FMNMX, ALU pipe) — an FFMA, an FMUL and two
 // FADDs with an |x| operand, all on the FMA pipe.  Three roundings per distance instead of one: t_far is padded by 5 ulp + pad.
 RTFS_HD bool slab_entry(const RaySlabs &r, float cx, float cy, float cz, float hx, float hy, float hz, float best_t, float &entry) {
-    const float tx = fmaf(cx, r.inv.x, r.noi.x), ux = fabsf(hx * r.inv.x);
-    const float ty = fmaf(cy, r.inv.y, r.noi.y), uy = fabsf(hy * r.inv.y);
-    const float tz = fmaf(cz, r.inv.z, r.noi.z), uz = fabsf(hz * r.inv.z);
-    float t_near = fmaxf(fmaxf(tx - ux, ty - uy), fmaxf(tz - uz, 0.0f));
-    float t_far = fmaf(fminf(fminf(tx + ux, ty + uy), tz + uz), 1.0000005960464478f, r.pad);
+    const float tx = fmaf(cx, r.inv.x, r.noi.x), ty = fmaf(cy, r.inv.y, r.noi.y), tz = fmaf(cz, r.inv.z, r.noi.z);
+    float t_near = fmaxf(fmaxf(fmaf(-hx, r.ainv.x, tx), fmaf(-hy, r.ainv.y, ty)), fmaxf(fmaf(-hz, r.ainv.z, tz), 0.0f));
+    float t_far = fmaf(fminf(fminf(fmaf(hx, r.ainv.x, tx), fmaf(hy, r.ainv.y, ty)), fmaf(hz, r.ainv.z, tz)), 1.0000005960464478f, r.pad);
     entry = t_near;
     return t_near <= fminf(t_far, best_t);
 }
