@@ -281,24 +281,15 @@ RTFS_HD bool sphere_hit(float3 o, float3 d, float4 s, bool self, float &t_out) {
     }
     float3 l = fma3(-b, d, oc);
     float disc = fmaf(s.w, s.w, -dot(l, l));
-    float ip;
-    if (fabsf(disc) < kTolF) { // Float.compare disc 0 = Equal
-        ip = -b;
-    } else if (disc < 0.0f) {
-        return false;
-    } else {
-        float im = sqrt_fast(disc); // disc >= 1e-8 here
-        float i1 = im - b, i2 = -(b + im);
-        bool p1 = i1 > kTolF, p2 = i2 > kTolF;
-        if (p1 && p2)
-            ip = (fabsf(i1 - i2) < kTolF || i1 < i2) ? i1 : i2;
-        else if (p1)
-            ip = i1;
-        else if (p2)
-            ip = i2;
-        else
-            return false;
-    }
+    // Sphere.fs:349-386 decides in three steps: Float.compare disc 0 (Equal: the one root -b; Less: miss), then which of
+    // i1 = -b + sqrt(disc), i2 = -b - sqrt(disc) is `positive`, then the smaller of two positive roots.  Since i2 <= i1,
+    // and they are 2 sqrt(disc) >= 2e-4 apart whenever disc >= 1e-8, that is: the root is i2 if i2 is positive, else i1,
+    // and the ray hits iff that root is positive — the same decisions in two compares and a select (the ALU pipe is
+    // the busiest unit of the render kernel).  disc within the tolerance of 0 is the case sqrt(disc) = 0 of the same formula.
+    if (disc <= -kTolF) return false;
+    const float im = disc < kTolF ? 0.0f : sqrt_fast(disc); // disc >= 1e-8 where the root is taken
+    const float i2 = -(b + im), i1 = im - b;
+    const float ip = i2 > kTolF ? i2 : i1;
     t_out = ip;
     return ip > kTolF;
 }
@@ -365,31 +356,18 @@ RTFS_HD bool sphere_hit_big_f32(float3 o, float3 d, float a, const DUnbounded &s
     }
     const float cf = big_sphere_c(o, s);
     const float disc = fmaf(bf, bf, -a * cf);
+    if (disc <= -kTolF) return false; // Float.compare disc 0 = Less
     float ip;
-    if (fabsf(disc) < kTolF) { // Float.compare disc 0 = Equal
+    if (disc < kTolF) { // Equal: the one root
         ip = -bf * inv_a;
-    } else if (disc < 0.0f) {
-        return false;
     } else {
-        float im = sqrt_fast(disc); // disc >= 1e-8 here
-        float q1 = im - bf, q2 = -(bf + im); // i1 = q1 / a (the larger root), i2 = q2 / a; q1 * q2 = a * c
-        float i1, i2;
-        if (bf < 0.0f) { // |q1| >= im >= 1e-4
-            i1 = q1 * inv_a;
-            i2 = cf * rcp_fast(q1);
-        } else { // |q2| >= im >= 1e-4
-            i2 = q2 * inv_a;
-            i1 = cf * rcp_fast(q2);
-        }
-        bool p1 = i1 > kTolF, p2 = i2 > kTolF;
-        if (p1 && p2)
-            ip = (fabsf(i1 - i2) < kTolF || i1 < i2) ? i1 : i2;
-        else if (p1)
-            ip = i1;
-        else if (p2)
-            ip = i2;
-        else
-            return false;
+        const float im = sqrt_fast(disc); // disc >= 1e-8 here
+        // i1 = q1 / a is the larger root, i2 = q2 / a the smaller; q1 * q2 = a * c gives whichever of them cancels in its
+        // own formula from the other.  As in sphere_hit: the root is i2 if it is positive, else i1 (they are >= 2e-4 apart).
+        const float q = bf < 0.0f ? im - bf : -(bf + im); // |q| >= im >= 1e-4
+        const float via_q = q * inv_a, via_c = cf * rcp_fast(q);
+        const float i1 = bf < 0.0f ? via_q : via_c, i2 = bf < 0.0f ? via_c : via_q;
+        ip = i2 > kTolF ? i2 : i1;
     }
     t_out = ip;
     return ip > kTolF;
