@@ -133,6 +133,19 @@ module internal Native =
     [<DllImport(Lib)>]
     extern void rt_multi_destroy (nativeint multi)
 
+    // one rank of a one-process-per-GPU job: the library issues the NCCL collectives itself (include/rtfs_b200.h, rt_comm_*)
+    [<DllImport(Lib)>]
+    extern int rt_comm_unique_id (byte[] idOut)
+
+    [<DllImport(Lib)>]
+    extern int rt_comm_create (byte[] id, int rank, int world, int device, nativeint stream, nativeint& comm)
+
+    [<DllImport(Lib)>]
+    extern int rt_comm_render (nativeint comm, nativeint scene, RtCamera& camera, int maxWidthCoord, int maxHeightCoord, RtRenderOpts& opts, byte[] rgbOut, nativeint sumsOut, RtStats& stats)
+
+    [<DllImport(Lib)>]
+    extern void rt_comm_destroy (nativeint comm)
+
     let check (rc : int) : unit =
         if rc <> 0 then
             failwithf "librtfs_b200 error %i: %s" rc (Marshal.PtrToStringAnsi (rt_last_error ()))
