@@ -363,8 +363,9 @@ def e2e_frames(r, spec, cam, n_e2e):
             h2d = sc.device_bytes()
             d2h = (rgb.nbytes if rgb is not None else 0) + 128
             sc.close()
+        own = time.perf_counter() - t0  # this rank's wall time from the common start; the collectives inside the frame tie the ranks together
         r.barrier()
-        dt, = r.reduce([time.perf_counter() - t0], "MAX")
+        dt, = r.reduce([own], "MAX")
         rr, h2d_all, d2h_all = r.reduce([rays, h2d, d2h], "SUM")
         if i >= 0:
             secs += dt

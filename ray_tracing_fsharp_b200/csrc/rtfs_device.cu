@@ -979,11 +979,29 @@ static int plan_launch(DeviceScene *ds, FrameParams &fp, bool probe, bool count,
     fp.stack_levels = int32_t(stack_q * 16 / (kBlockThreads * 4));
     plan.smem_bytes = (used_q + (sstack ? stack_q : 0)) * 16;
     fn = flow ? (probe ? pick_flow<true>(smem, count) : pick_flow<false>(smem, count)) : pick_kernel(probe, smem, count, sstack, wide);
-    RT_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(plan.smem_bytes)));
-    int per_sm = 0;
-    RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)fn, kBlockThreads, plan.smem_bytes));
-    if (per_sm < 1) return fail(RT_ERR_CUDA, "render kernel does not fit on an SM");
-    plan.blocks = per_sm * ds->ws->sm_count;
+    { // the attribute and the occupancy of a (kernel, shared-memory size, device) triple never change: ask once
+        struct Known {
+            const void *fn;
+            size_t smem;
+            int device, per_sm;
+        };
+        static std::mutex mutex;
+        static std::vector<Known> known;
+        int per_sm = -1;
+        {
+            std::lock_guard<std::mutex> lock(mutex);
+            for (const Known &k : known)
+                if (k.fn == (const void *)fn && k.smem == plan.smem_bytes && k.device == ds->device) per_sm = k.per_sm;
+        }
+        if (per_sm < 0) {
+            RT_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(plan.smem_bytes)));
+            RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)fn, kBlockThreads, plan.smem_bytes));
+            std::lock_guard<std::mutex> lock(mutex);
+            known.push_back(Known{(const void *)fn, plan.smem_bytes, ds->device, per_sm});
+        }
+        if (per_sm < 1) return fail(RT_ERR_CUDA, "render kernel does not fit on an SM");
+        plan.blocks = per_sm * ds->ws->sm_count;
+    }
     return RT_OK;
 }
 
@@ -1151,6 +1169,22 @@ using namespace rtfs;
 // C ABI — device entry points
 // =================================================================================================
 extern "C" {
+
+int rt_host_pin(void *ptr, size_t bytes) {
+    if (!ptr || !bytes) return fail(RT_ERR_INVALID_ARGUMENT, "rt_host_pin: null or empty buffer");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return fail(RT_ERR_NO_DEVICE, "rt_host_pin: no CUDA device is visible");
+    }
+    RT_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    return RT_OK;
+}
+int rt_host_unpin(void *ptr) {
+    if (!ptr) return fail(RT_ERR_INVALID_ARGUMENT, "rt_host_unpin: null buffer");
+    RT_CUDA(cudaHostUnregister(ptr));
+    return RT_OK;
+}
 
 int rt_device_count(void) {
     int n = 0;

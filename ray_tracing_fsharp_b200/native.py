@@ -33,6 +33,8 @@ def _declare(lib):
         "rt_abi_version": (C.c_int, []),
         "rt_last_error": (C.c_char_p, []),
         "rt_device_count": (C.c_int, []),
+        "rt_host_pin": (C.c_int, [_vp, C.c_size_t]),
+        "rt_host_unpin": (C.c_int, [_vp]),
         "rt_camera_make_basic": (C.c_int, [_i32, C.c_double, C.c_double, _vp, _vp, _vp, C.POINTER(RtCamera)]),
         "rt_ppm_format": (C.c_int, [_vp, _i32, _i32, _i32, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
         "rt_ppm_write_file": (C.c_int, [_vp, _i32, _i32, _i32, C.c_char_p]),
@@ -133,9 +135,21 @@ class FrameRing:
             raise ValueError("FrameRing needs at least one frame")
         self.shape = tuple(shape)
         self._frames = [np.zeros(self.shape, np.uint8) for _ in range(count)]
+        self._pinned = []
         for f in self._frames:
             f.fill(0)  # touch the pages now
+            # page-lock it where a device is present (rt_host_pin): the device->host copy then runs at PCIe speed
+            if lib().rt_host_pin(C.c_void_p(f.ctypes.data), f.nbytes) == abi.RT_OK:
+                self._pinned.append(f)
         self._at = 0
+
+    def __del__(self):
+        try:
+            for f in self._pinned:
+                lib().rt_host_unpin(C.c_void_p(f.ctypes.data))
+            self._pinned = []
+        except Exception:
+            pass
 
     def next(self):
         f = self._frames[self._at % len(self._frames)]
