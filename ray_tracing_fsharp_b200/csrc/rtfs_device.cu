@@ -979,24 +979,30 @@ static int plan_launch(DeviceScene *ds, FrameParams &fp, bool probe, bool count,
     fp.stack_levels = int32_t(stack_q * 16 / (kBlockThreads * 4));
     plan.smem_bytes = (used_q + (sstack ? stack_q : 0)) * 16;
     fn = flow ? (probe ? pick_flow<true>(smem, count) : pick_flow<false>(smem, count)) : pick_kernel(probe, smem, count, sstack, wide);
-    { // the attribute and the occupancy of a (kernel, shared-memory size, device) triple never change: ask once
+    { // The dynamic shared-memory limit of a kernel is a per-function, per-device setting: it is only ever RAISED here
+      // (to the largest size any scene has asked for), and the occupancy of a (kernel, size, device) triple is asked once.
         struct Known {
             const void *fn;
             size_t smem;
             int device, per_sm;
         };
         static std::mutex mutex;
-        static std::vector<Known> known;
-        int per_sm = -1;
-        {
-            std::lock_guard<std::mutex> lock(mutex);
-            for (const Known &k : known)
-                if (k.fn == (const void *)fn && k.smem == plan.smem_bytes && k.device == ds->device) per_sm = k.per_sm;
-        }
-        if (per_sm < 0) {
+        static std::vector<Known> known; // smem = the size the entry's occupancy was computed for
+        static std::vector<Known> limits; // smem = the limit currently set for (fn, device)
+        std::lock_guard<std::mutex> lock(mutex);
+        Known *limit = nullptr;
+        for (Known &k : limits)
+            if (k.fn == (const void *)fn && k.device == ds->device) limit = &k;
+        if (!limit || limit->smem < plan.smem_bytes) {
             RT_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(plan.smem_bytes)));
+            if (limit) limit->smem = plan.smem_bytes;
+            else limits.push_back(Known{(const void *)fn, plan.smem_bytes, ds->device, 0});
+        }
+        int per_sm = -1;
+        for (const Known &k : known)
+            if (k.fn == (const void *)fn && k.smem == plan.smem_bytes && k.device == ds->device) per_sm = k.per_sm;
+        if (per_sm < 0) {
             RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)fn, kBlockThreads, plan.smem_bytes));
-            std::lock_guard<std::mutex> lock(mutex);
             known.push_back(Known{(const void *)fn, plan.smem_bytes, ds->device, per_sm});
         }
         if (per_sm < 1) return fail(RT_ERR_CUDA, "render kernel does not fit on an SM");
