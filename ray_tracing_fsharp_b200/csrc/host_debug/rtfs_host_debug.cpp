@@ -219,6 +219,53 @@ int dbg_render_logged(const RtHittable *objects, int n_objects, const RtTexture 
     return rc;
 }
 
+// The order of node visits ('I') and leaf visits ('L') of every ray of a frame, rays separated by '.', for the warp
+// simulations under profiles/ (what batching the leaf visits of a warp would buy).  Walks the binary tree exactly as
+// bvh_closest does, visit by visit.
+int dbg_visit_trace(const RtHittable *objects, int n_objects, const RtTexture *textures, int n_textures, const RtCamera *camera, int max_w,
+                    int max_h, uint64_t seed, int spp, char *out, uint64_t cap, uint64_t *len) {
+    HostScene hs;
+    int rc = build(hs, objects, n_objects, textures, n_textures, 0);
+    if (rc != RT_OK) return rc;
+    SceneAccess<false> sc;
+    sc.g = hs.g;
+    sc.s_nodes = sc.s_spheres = sc.s_mats = 0;
+    const DevCamera cam = dev_camera(*camera, max_w, max_h);
+    uint64_t n = 0;
+    auto emit = [&](char c) {
+        if (n < cap) out[n] = c;
+        ++n;
+    };
+    for (int r = 0; r < cam.rows; ++r)
+        for (int c = 0; c < cam.cols; ++c)
+            for (int j = 0; j < spp; ++j) {
+                PathState ps;
+                if (!path_begin(ps, cam, uint32_t(seed), uint32_t(seed >> 32), r, c, uint32_t(j))) continue;
+                for (;;) {
+                    TraversalCounters cn{0, 0};
+                    LocalStack stack;
+                    float best_t = kNoHitT;
+                    int best_ref = kNoRef;
+                    if (sc.g.n_bounded > 0) {
+                        const RaySlabs rs = make_slabs(ps.o, ps.d);
+                        int sp = 0, node = sc.root();
+                        for (;;) {
+                            emit(node >= 0 ? 'I' : 'L');
+                            if (bvh_visit<false, true>(sc, rs, ps.o, ps.d, ps.last, node, sp, stack, best_t, best_ref, cn)) break;
+                        }
+                    }
+                    emit('.');
+                    Hit h = finish_hit<false, true>(sc, ps.o, ps.d, ps.last, best_t, best_ref, cn);
+                    uint32_t result;
+                    if (path_after_hit<false>(ps, sc, h, cam.depth, result)) break;
+                }
+                emit('/'); // end of path
+            }
+    *len = n;
+    rt_scene_destroy(hs.scene);
+    return RT_OK;
+}
+
 // hitObject through both trees for explicit rays: prim_out = index into the caller's Hittable array, or -1
 int dbg_hit_object(const RtHittable *objects, int n_objects, int wide, int n, const float *o, const float *d, int32_t *prim_out, float *t_out) {
     HostScene hs;
