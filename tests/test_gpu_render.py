@@ -199,6 +199,25 @@ def test_flow_and_lockstep_schedules_agree_bit_for_bit(which):
         assert np.array_equal(s1, s2), (which, spp)
 
 
+def test_stats_of_a_frame_and_page_locked_output_frames():
+    """RtStats of rt_render (the main-phase kernel's own time and rays, no degenerate paths on a well-formed scene), and
+    native.FrameRing: explicitly recycled, page-locked output arrays (rt_host_pin) receive the same frame as a fresh one."""
+    spec = _small("C2", 60, 40, 32)
+    osc, dsc, cam = scene_pair(spec)
+    mw, mh = spec.max_width_coord, spec.max_height_coord
+    a, _, st = dsc.render(cam, mw, mh, seed=21)
+    assert 0 < st.main_rays < st.rays and 0.0 < st.main_ms <= st.kernel_ms <= st.total_ms and st.degenerate_paths == 0
+    ring = native.FrameRing((spec.rows, spec.cols, 3), count=2)
+    f0 = ring.next()
+    b, _, _ = dsc.render(cam, mw, mh, seed=21, rgb_out=f0)
+    assert b is f0 and np.array_equal(a, b)
+    f1 = ring.next()
+    c, _, _ = dsc.render(cam, mw, mh, seed=22, rgb_out=f1)
+    assert c is f1 and c is not b and not np.array_equal(b, c) and np.array_equal(a, f0)  # the earlier frame is untouched
+    assert ring.next() is f0
+    assert native.lib().rt_host_unpin(None) == abi.RT_ERR_INVALID_ARGUMENT
+
+
 def test_hot_pink_when_the_bounce_budget_runs_out():
     """F3: a path that is still alive after maxCount + 1 interactions is HotPink, a miss is Black."""
     from ray_tracing_fsharp_b200.domain import Colour, Hittable, Pixel, Sphere, SphereStyle, Texture

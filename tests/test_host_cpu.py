@@ -143,6 +143,27 @@ def test_sah_tree_is_a_valid_bvh(which):
         check(0)
 
 
+@pytest.mark.parametrize("which", ["reduced", "C1", "C2", "C4", "mid"])
+def test_wide_bvh_is_valid_on_the_host(which):
+    """rt_scene_wide_bvh_check: the 8-wide compressed tree (RT_FLAG_WIDE_BVH) holds every bounded sphere of non-negative
+    radius exactly once and every decoded (quantised) box contains what lies below it; at most 8 children per node."""
+    if which == "reduced":
+        spec = small_random_spheres()
+    elif which == "mid":
+        spec = sample_images.many_spheres(n=3000)
+    else:
+        spec = sample_images.CONFIGS[which]()
+    hs, ts, keep = marshal(spec.objects)
+    h = native.SceneHandle(hs, ts, -1, keepalive=keep)
+    info = h.wide_bvh_check()
+    n_spheres = sum(1 for o in spec.objects if isinstance(o, Hittable.Sphere) and o.sphere.Radius >= 0)
+    assert info["spheres"] == n_spheres
+    assert 1 <= info["nodes"] <= max(1, n_spheres) and 1.0 <= info["mean_children"] <= 8.0
+    assert info["depth"] <= 12
+    again = h.wide_bvh_check()  # idempotent
+    assert again == info
+
+
 def test_scene_create_validates_like_the_type_system_would():
     lib = native.lib()
 
