@@ -451,6 +451,7 @@ def run_ours(args):
         others[name] = entry
         oh.close()
 
+    peer_memory = r.comm.uses_peer_memory()
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -482,8 +483,8 @@ def run_ours(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["ms"] / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(spec, r.adaptive), "l2": "flushed between steps (256 MiB fill)",
-                       "parallelism": f"sample-split x{world}" + (", collectives issued by librtfs_b200.so (rt_comm_render): NCCL all-reduce of flags (uint8 max), "
-                                                                    "reduce-scatter of sums (int32), all-gather of RGB8" if world > 1 else ""),
+                       "parallelism": f"sample-split x{world}" + (", exchange steps issued by librtfs_b200.so (rt_comm_render): NCCL all-reduce of the flags (uint8 max); "
+                                                                    "the sums reduced, divided and gathered as config.frame_tail says" if world > 1 else ""),
                        "scene_bytes_staged_in_shared_memory": 0 if args.no_smem else handle.shared_memory_bytes()},
             "rays_per_step": m["rays"] / args.steps, "paths_per_step": m["paths"] / args.steps, "degenerate_paths": m["degenerate"],
             "e2e": {"value": e2e["rays"] / e2e["secs"] / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
@@ -515,6 +516,8 @@ def run_ours(args):
         if world > 1:
             v, path = native.CommHandle.nccl_version()
             line["config"]["nccl"] = f"{v} bound by librtfs_b200.so from {path}"
+            line["config"]["frame_tail"] = ("one kernel over NVLink peer memory (CUDA IPC): sum over ranks, divide, gamma, gather; two 4-byte all-reduces as barriers"
+                                            if peer_memory else "ncclReduceScatter + finalize_kernel + ncclAllGather (peer mapping unavailable)")
         if cpu:
             line["cpu_baseline"] = {k: v for k, v in cpu.items() if k != "counters"}
         print(json.dumps(line), flush=True)

@@ -279,7 +279,8 @@ int rt_device_finalize(int32_t device, const int32_t *d_stats, int32_t n_pixels,
  * the scene: rank r probes its share of the tiles (Scene.fs:172-188), the flags are all-reduced (MAX), rank r
  * adds its share of the remaining sample indices (Scene.fs:191-192), the PixelStats sums are reduce-scattered
  * (int32 SUM) so that every rank divides (Pixel.fs:103-108) and gamma-corrects (ImageOutput.fs:11-18) one slice
- * of the pixels, and the RGB8 slices are all-gathered.  All of it — kernels and NCCL calls — is enqueued by
+ * of the pixels, and the RGB8 slices are all-gathered (as ONE kernel over NVLink peer memory where the ranks' buffers can
+ * be mapped into one another, see rt_comm_uses_peer_memory; else with ncclReduceScatter / ncclAllGather).  All of it — kernels and NCCL calls — is enqueued by
  * rt_comm_render on one stream; the image is bit-identical to rt_render's for every world size.
  * NCCL (libnccl.so.2) is bound at run time on first use: RT_ERR_UNSUPPORTED if it cannot be loaded.
  *
@@ -291,7 +292,12 @@ typedef struct RtComm RtComm;
 int rt_comm_unique_id(uint8_t *id_out /* RT_COMM_ID_BYTES */);
 int rt_comm_create(const uint8_t *id, int32_t rank, int32_t world, int32_t device, void *stream,
                    RtComm **out);
-void rt_comm_destroy(RtComm *comm);
+void rt_comm_destroy(RtComm *comm); /* collective, like rt_comm_create */
+/* 1 when the ranks' sum and frame buffers are mapped into one another (CUDA IPC over NVLink peer access) and the tail of a
+ * frame — sum over ranks, divide, gamma, gather — is ONE kernel of peer loads and peer stores between two 4-byte barriers;
+ * 0 when that mapping was refused on some rank (or RTFS_COMM_NO_PEER=1) and the tail is ncclReduceScatter + finalize +
+ * ncclAllGather.  Decided collectively whenever the communicator (re)allocates its buffers. */
+int rt_comm_uses_peer_memory(const RtComm *comm);
 /* version (e.g. 22809) and file name of the NCCL build the library bound */
 int rt_comm_nccl_version(int32_t *version_out, char *path_out, size_t path_cap);
 /* One frame (collective: every rank calls it with the same camera, extents and opts, on its own replica of the

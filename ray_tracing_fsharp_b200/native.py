@@ -61,6 +61,7 @@ def _declare(lib):
         "rt_comm_unique_id": (C.c_int, [_vp]),
         "rt_comm_create": (C.c_int, [_vp, _i32, _i32, _i32, _vp, C.POINTER(_vp)]),
         "rt_comm_destroy": (None, [_vp]),
+        "rt_comm_uses_peer_memory": (C.c_int, [_vp]),
         "rt_comm_nccl_version": (C.c_int, [C.POINTER(_i32), C.c_char_p, C.c_size_t]),
         "rt_comm_render": (C.c_int, [_vp, _vp, C.POINTER(RtCamera), _i32, _i32, C.POINTER(RtRenderOpts), _vp, _vp, C.POINTER(RtStats)]),
         "rt_comm_last_stats": (C.c_int, [_vp, _vp, C.POINTER(RtStats)]),
@@ -369,6 +370,9 @@ class CommHandle:
         check(lib().rt_comm_render(self.ptr, scene.ptr, C.byref(camera), max_w, max_h, C.byref(opts), ptr(rgb), ptr(sums),
                                    C.byref(stats) if stats is not None else None))
         return rgb, sums, stats
+
+    def uses_peer_memory(self) -> bool:
+        return bool(lib().rt_comm_uses_peer_memory(self.ptr))
 
     def last_stats(self, scene: "SceneHandle"):
         """Timing / counters of the last enqueue-only render (call after synchronising the stream)."""

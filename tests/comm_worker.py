@@ -52,6 +52,7 @@ def main():
     same = torch.tensor([int(torch.equal(mine, ref))], device="cuda")
     dist.all_reduce(same, op=dist.ReduceOp.MIN)
     results["all_ranks_hold_the_frame"] = np.array([int(same.item())])
+    results["peer_memory"] = np.array([int(comm.uses_peer_memory())])
     if rank == 0:
         np.savez(out_path, **results)
     scene.close()

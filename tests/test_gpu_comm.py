@@ -49,11 +49,18 @@ def test_single_rank_communicator_equals_rt_render(which):
         comm.close()
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
-def test_ranks_over_nccl_equal_rt_render(world):
-    """One process per GPU under torchrun; the library all-reduces the flags, reduce-scatters the sums, all-gathers RGB8."""
+@pytest.mark.parametrize("world,tail", [(2, "peer"), (2, "nccl"), (4, "peer"), (8, "peer")])
+def test_ranks_over_nccl_equal_rt_render(world, tail):
+    """One process per GPU under torchrun; the library all-reduces the flags and finishes the frame either with ONE kernel
+    over NVLink peer memory (the ranks' buffers mapped with CUDA IPC) or, with RTFS_COMM_NO_PEER=1, with ncclReduceScatter +
+    finalize + ncclAllGather.  Both must reproduce rt_render bit for bit."""
     if native.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
+    env = dict(os.environ)
+    if tail == "nccl":
+        env["RTFS_COMM_NO_PEER"] = "1"
+    else:
+        env.pop("RTFS_COMM_NO_PEER", None)
     for which in ("reduced", "C3"):
         spec = _spec(which)
         _osc, dsc, cam = scene_pair(spec)
@@ -62,7 +69,7 @@ def test_ranks_over_nccl_equal_rt_render(world):
             out = os.path.join(td, "frame.npz")
             cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
                    "--master-port", str(29500 + world), os.path.join(HERE, "comm_worker.py"), out, which]
-            res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+            res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
             assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
             got = np.load(out)
             for k, adaptive in (("a", True), ("f", False)):
@@ -73,3 +80,7 @@ def test_ranks_over_nccl_equal_rt_render(world):
                 assert np.array_equal(got[f"rgb_gamma_{k}"], rgb_g)
                 assert int(got[f"work_{k}"][0]) == int(st.rays) and int(got[f"work_{k}"][1]) == int(st.paths)
             assert int(got["all_ranks_hold_the_frame"][0]) == 1
+            if tail == "nccl":
+                assert int(got["peer_memory"][0]) == 0
+            else:
+                print(f"world {world}: peer memory {'mapped' if int(got['peer_memory'][0]) else 'REFUSED (NCCL tail used)'}")
