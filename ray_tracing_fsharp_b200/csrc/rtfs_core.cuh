@@ -234,7 +234,7 @@ RTFS_HD float3 inverse_directions(float3 d) { return f3(1.0f / d.x, 1.0f / d.y, 
 
 // Slab test of the render traversal.  Per ray: inv = 1 / d (components clamped away from zero, so no
 // 0 * inf = NaN arises), noi = -o * inv, and pad = an absolute bound on the rounding of c * inv + noi; per box:
-// twelve FMA-pipe operations and five min / max / compare (see slab_entry).  Conservative: boxes are rounded outwards on
+// ten packed FMA-pipe operations and a handful of min / max / compare for both children (see slab_pair).  Conservative: boxes are rounded outwards on
 // the host, t_far is padded by 5 ulp (Ize, "Robust BVH Ray Traversal") plus `pad`.  Returns the entry distance for ordering and culls against the best hit so far
 // (a finite number: kNoHitT while nothing is hit, so that the box {+inf, +inf} of a one-leaf tree is never
 // entered).  It may accept a box the reference rejects only for rays within rounding of a box face; closest-hit
@@ -256,15 +256,48 @@ RTFS_HD RaySlabs make_slabs(float3 o, float3 d) {
     r.pad = 7.2e-7f * fmaxf(fmaxf(fabsf(r.noi.x), fabsf(r.noi.y)), fabsf(r.noi.z));
     return r;
 }
-// The box comes as centre c and half-extent h >= 0 (rtfs_internal.h, device_node_of): per axis the two plane distances are
-// t_c -+ |h inv| with t_c = c inv + noi, so near and far need no min / max pair (FMNMX, ALU pipe) — an FFMA, an FMUL and two
-// FADDs with an |x| operand, all on the FMA pipe.  Three roundings per distance instead of one: t_far is padded by 5 ulp + pad.
-RTFS_HD bool slab_entry(const RaySlabs &r, float cx, float cy, float cz, float hx, float hy, float hz, float best_t, float &entry) {
-    const float tx = fmaf(cx, r.inv.x, r.noi.x), ty = fmaf(cy, r.inv.y, r.noi.y), tz = fmaf(cz, r.inv.z, r.noi.z);
-    float t_near = fmaxf(fmaxf(fmaf(-hx, r.ainv.x, tx), fmaf(-hy, r.ainv.y, ty)), fmaxf(fmaf(-hz, r.ainv.z, tz), 0.0f));
-    float t_far = fmaf(fminf(fminf(fmaf(hx, r.ainv.x, tx), fmaf(hy, r.ainv.y, ty)), fmaf(hz, r.ainv.z, tz)), 1.0000005960464478f, r.pad);
-    entry = t_near;
-    return t_near <= fminf(t_far, best_t);
+// Two FP32 fused multiply-adds in one instruction: fma.rn.f32x2 (sm_100, SASS FFMA2) on register pairs, each half rounded
+// exactly as fmaf rounds.  The render kernel is bound by instruction issue, not by the FMA pipe, so halving the issue slots
+// of the slab arithmetic pays.  An operand whose halves are the same value (or the same value under |x| / -x) costs no extra
+// register: ptxas folds the pack into a broadcast operand of FFMA2 (`|R27|.F32`).
+RTFS_HD void fma2(float ax, float ay, float bx, float by, float cx, float cy, float &rx, float &ry) {
+#ifdef __CUDA_ARCH__
+    asm("{\n\t.reg .b64 a, b, c, r;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %5};\n\tmov.b64 c, {%6, %7};\n\t"
+        "fma.rn.f32x2 r, a, b, c;\n\tmov.b64 {%0, %1}, r;\n\t}"
+        : "=f"(rx), "=f"(ry)
+        : "f"(ax), "f"(ay), "f"(bx), "f"(by), "f"(cx), "f"(cy));
+#else
+    rx = fmaf(ax, bx, cx);
+    ry = fmaf(ay, by, cy);
+#endif
+}
+// The two child boxes of a node at once.  Boxes come as centre c and half-extent h >= 0 with the left and the right child's
+// values side by side (rtfs_internal.h, device_node_of): per axis the plane distances are t_c -+ h |inv| with t_c = c inv + noi,
+// so near and far need no min / max pair (FMNMX, ALU pipe), and each of the three steps is one FFMA2 per axis for both
+// boxes: ten FMA-pipe instructions per visit with the padding.  Three roundings per distance instead of one: t_far is padded
+// by 5 ulp + pad.  hit = t_near <= min(t_far, best_t); the entry distances order the descent.
+RTFS_HD void slab_pair(const RaySlabs &r, const uint4 &q0, const uint4 &q1, const uint4 &q2, float best_t, bool &hit_l, bool &hit_r, float &entry_l,
+                       float &entry_r) {
+    const float cxl = __uint_as_float(q0.x), cxr = __uint_as_float(q0.y), cyl = __uint_as_float(q0.z), cyr = __uint_as_float(q0.w);
+    const float czl = __uint_as_float(q1.x), czr = __uint_as_float(q1.y), hxl = __uint_as_float(q1.z), hxr = __uint_as_float(q1.w);
+    const float hyl = __uint_as_float(q2.x), hyr = __uint_as_float(q2.y), hzl = __uint_as_float(q2.z), hzr = __uint_as_float(q2.w);
+    float txl, txr, tyl, tyr, tzl, tzr;
+    fma2(cxl, cxr, r.inv.x, r.inv.x, r.noi.x, r.noi.x, txl, txr);
+    fma2(cyl, cyr, r.inv.y, r.inv.y, r.noi.y, r.noi.y, tyl, tyr);
+    fma2(czl, czr, r.inv.z, r.inv.z, r.noi.z, r.noi.z, tzl, tzr);
+    float nxl, nxr, nyl, nyr, nzl, nzr, fxl, fxr, fyl, fyr, fzl, fzr;
+    fma2(hxl, hxr, -r.ainv.x, -r.ainv.x, txl, txr, nxl, nxr);
+    fma2(hyl, hyr, -r.ainv.y, -r.ainv.y, tyl, tyr, nyl, nyr);
+    fma2(hzl, hzr, -r.ainv.z, -r.ainv.z, tzl, tzr, nzl, nzr);
+    fma2(hxl, hxr, r.ainv.x, r.ainv.x, txl, txr, fxl, fxr);
+    fma2(hyl, hyr, r.ainv.y, r.ainv.y, tyl, tyr, fyl, fyr);
+    fma2(hzl, hzr, r.ainv.z, r.ainv.z, tzl, tzr, fzl, fzr);
+    float fl, fr;
+    fma2(fminf(fminf(fxl, fyl), fzl), fminf(fminf(fxr, fyr), fzr), 1.0000005960464478f, 1.0000005960464478f, r.pad, r.pad, fl, fr);
+    entry_l = fmaxf(fmaxf(nxl, nyl), fmaxf(nzl, 0.0f));
+    entry_r = fmaxf(fmaxf(nxr, nyr), fmaxf(nzr, 0.0f));
+    hit_l = entry_l <= fminf(fl, best_t);
+    hit_r = entry_r <= fminf(fr, best_t);
 }
 
 // ---- Sphere.firstIntersection (Sphere.fs:349-386) -------------------------------------------------------
@@ -591,10 +624,8 @@ RTFS_HD bool bvh_visit(const SceneAccess<SMEM> &sc, const RaySlabs &rs, float3 o
         uint4 q0, q1, q2, q3;
         sc.node(node, q0, q1, q2, q3);
         float tl, tr;
-        bool hl = slab_entry(rs, __uint_as_float(q0.x), __uint_as_float(q0.y), __uint_as_float(q0.z), __uint_as_float(q0.w),
-                             __uint_as_float(q1.x), __uint_as_float(q1.y), best_t, tl);
-        bool hr = slab_entry(rs, __uint_as_float(q1.z), __uint_as_float(q1.w), __uint_as_float(q2.x), __uint_as_float(q2.y),
-                             __uint_as_float(q2.z), __uint_as_float(q2.w), best_t, tr);
+        bool hl, hr;
+        slab_pair(rs, q0, q1, q2, best_t, hl, hr, tl, tr);
         if (COUNT) cn.box_tests += 2;
         int left = int(q3.x), right = int(q3.y);
         if (hl && hr) {

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <limits>
@@ -430,9 +431,11 @@ void classify_unbounded(DUnbounded &u) {
     }
 }
 
-// min / max boxes -> centre / half-extent boxes (see rtfs_internal.h), never smaller than the original
+// min / max boxes -> centre / half-extent boxes in the paired layout the device reads (see rtfs_internal.h), never smaller
+// than the original
 DNode device_node_of(const DNode &n) {
     DNode d = n;
+    float c[2][3], h[2][3];
     auto conv = [](const float *mn, const float *mx, float *c_out, float *h_out) {
         for (int a = 0; a < 3; ++a) {
             if (!std::isfinite(mn[a]) || !std::isfinite(mx[a])) { // the never-entered dummy box of a one-sphere tree
@@ -440,15 +443,23 @@ DNode device_node_of(const DNode &n) {
                 h_out[a] = 0.f;
                 continue;
             }
-            float c = float(0.5 * (double(mn[a]) + double(mx[a])));
-            double h = std::max(double(mx[a]) - double(c), double(c) - double(mn[a]));
-            float hf = round_up(h);
-            c_out[a] = c;
+            float cf = float(0.5 * (double(mn[a]) + double(mx[a])));
+            double hd = std::max(double(mx[a]) - double(cf), double(cf) - double(mn[a]));
+            float hf = round_up(hd);
+            c_out[a] = cf;
             h_out[a] = std::nextafterf(hf, std::numeric_limits<float>::infinity());
         }
     };
-    conv(n.l_mn, n.l_mx, d.l_mn, d.l_mx); // l_mn now holds the centre, l_mx the half-extent
-    conv(n.r_mn, n.r_mx, d.r_mn, d.r_mx);
+    conv(n.l_mn, n.l_mx, c[0], h[0]);
+    conv(n.r_mn, n.r_mx, c[1], h[1]);
+    // {c.x l, c.x r, c.y l, c.y r | c.z l, c.z r, h.x l, h.x r | h.y l, h.y r, h.z l, h.z r}: the twelve floats of the struct in order
+    float *q = d.l_mn;
+    static_assert(offsetof(DNode, left) == 12 * sizeof(float), "the twelve box floats are contiguous");
+    for (int a = 0; a < 3; ++a)
+        for (int side = 0; side < 2; ++side) {
+            q[2 * a + side] = c[side][a];
+            q[6 + 2 * a + side] = h[side][a];
+        }
     return d;
 }
 

@@ -43,12 +43,14 @@ struct DNode {
     int32_t pad0, pad1;
 };
 static_assert(sizeof(DNode) == 64, "DNode must be 64 bytes");
-// What the DEVICE holds per node: the same two boxes as centre and half-extent (same 64 bytes, same quad layout with
-// {c.x, c.y, c.z, h.x | h.y, h.z, ...}).  For a ray with reciprocal direction inv and noi = -o * inv the slab distances of
-// an axis are then  t_c -+ |h * inv|  with t_c = c * inv + noi: one FFMA, one FMUL and two FADDs with an |x| operand
-// modifier, all on the FMA pipe — where the min / max form needs two FFMAs and two FMNMX on the ALU pipe, the busiest
-// unit of the render kernel (67 % against 29 % for the FMA pipe, ncu).  device_node_of() converts, rounding the half-extent
-// upwards so that the box never shrinks.
+// What the DEVICE holds per node: the same two boxes as centre c and half-extent h >= 0, left and right child side by side
+// (same 64 bytes):
+//   q0 = {c.x l, c.x r, c.y l, c.y r}   q1 = {c.z l, c.z r, h.x l, h.x r}   q2 = {h.y l, h.y r, h.z l, h.z r}   q3 as above
+// For a ray with reciprocal direction inv and noi = -o * inv the slab distances of an axis are  t_c -+ h |inv|  with
+// t_c = c * inv + noi: near and far come out ordered, so no min / max pair per axis (ALU pipe) is needed, and because the two
+// children's values sit in adjacent, even-aligned registers after a 128-bit load, each step is ONE packed FFMA2
+// (fma.rn.f32x2, sm_100) for both boxes with the ray's constant as a broadcast operand: ten FMA-pipe instructions per visit
+// (slab_pair, rtfs_core.cuh).  device_node_of() converts, rounding the half-extent upwards so that the box never shrinks.
 DNode device_node_of(const DNode &minmax);
 
 // Per-primitive material record, 32 B = two 128-bit loads.  Index = device primitive id.
