@@ -144,6 +144,7 @@ DevCamera dev_camera(const RtCamera &c, int max_w, int max_h) { // = make_dev_ca
 // optional trace of the work per ray (slab tests, primitive tests), path by path: feeds the warp-scheduling
 // simulations under profiles/ (how much of a warp's time is lost to the longest walk of its 32 lanes)
 std::vector<uint32_t> *g_ray_log = nullptr;
+std::vector<float> *g_ray_geometry = nullptr; // with it: origin, direction and bounce index of every logged ray (7 floats)
 
 template <bool WIDE>
 uint32_t trace_one(const SceneAccess<false> &sc, const DevCamera &cam, uint64_t seed, int r, int c, uint32_t sample, uint64_t &rays) {
@@ -155,6 +156,7 @@ uint32_t trace_one(const SceneAccess<false> &sc, const DevCamera &cam, uint64_t 
     for (;;) {
         ++rays;
         const TraversalCounters before = cn;
+        if (g_ray_geometry) g_ray_geometry->insert(g_ray_geometry->end(), {ps.o.x, ps.o.y, ps.o.z, ps.d.x, ps.d.y, ps.d.z, float(ps.bounces)});
         const bool done = path_step<false, true, LocalStack, WIDE>(ps, sc, cam.depth, result, cn, 1u, stack);
         if (g_ray_log) g_ray_log->push_back(((cn.box_tests - before.box_tests) << 8) | ((cn.prim_tests - before.prim_tests) & 255u) | (done ? 0x80000000u : 0u));
         if (done) break;
@@ -216,6 +218,20 @@ int dbg_render_logged(const RtHittable *objects, int n_objects, const RtTexture 
     g_ray_log = nullptr;
     *log_len = log.size();
     std::memcpy(log_out, log.data(), sizeof(uint32_t) * std::min<uint64_t>(log_cap, log.size()));
+    return rc;
+}
+
+// dbg_render_logged plus the geometry of every ray (7 floats per ray: origin, direction, bounce index), for the experiments
+// under profiles/ that ask how well a ray's walk length can be predicted before the walk
+int dbg_render_logged_geometry(const RtHittable *objects, int n_objects, const RtTexture *textures, int n_textures, const RtCamera *camera,
+                               int max_w, int max_h, uint64_t seed, int adaptive, uint8_t *rgb_out, int32_t *sums_out, uint32_t *log_out,
+                               float *geometry_out, uint64_t log_cap, uint64_t *log_len) {
+    std::vector<float> geometry;
+    g_ray_geometry = &geometry;
+    int rc = dbg_render_logged(objects, n_objects, textures, n_textures, camera, max_w, max_h, seed, adaptive, 0, rgb_out, sums_out, log_out, log_cap,
+                               log_len);
+    g_ray_geometry = nullptr;
+    std::memcpy(geometry_out, geometry.data(), sizeof(float) * 7 * std::min<uint64_t>(log_cap, geometry.size() / 7));
     return rc;
 }
 

@@ -460,6 +460,11 @@ RTFS_HD float4 ldg_sphere(const float4 *p) {
 #endif
 }
 
+// A staged node takes FIVE quads of shared memory, not four: with a stride of 64 bytes quad q of every node lies in one
+// of only two 16-byte bank groups, so the LDS.128 of a walk's divergent lanes (each at a node of its own) collide several
+// ways within every quarter-warp (ncu: 39 % of all shared-memory wavefronts were bank conflicts).  At 80 bytes quad q of node
+// i starts at bank group (5 i + q) mod 8: every group equally likely.  Child refs are byte addresses, so a visit pays nothing.
+constexpr uint32_t kStagedNodeQuads = 5;
 template <bool SMEM>
 struct SceneAccess {
     SceneGlobal g;
@@ -515,10 +520,10 @@ struct SceneAccess {
         for (int i = threadIdx.x; i < n_nodes_q; i += blockDim.x) {
             uint4 v = __ldg(g.nodes + i);
             if ((i & 3) == 3) { // {left, right, -, -}
-                v.x = int(v.x) >= 0 ? s_nodes + 64u * v.x : uint32_t(ref_of_sphere(~int(v.x)));
-                v.y = int(v.y) >= 0 ? s_nodes + 64u * v.y : uint32_t(ref_of_sphere(~int(v.y)));
+                v.x = int(v.x) >= 0 ? s_nodes + 16u * kStagedNodeQuads * v.x : uint32_t(ref_of_sphere(~int(v.x)));
+                v.y = int(v.y) >= 0 ? s_nodes + 16u * kStagedNodeQuads * v.y : uint32_t(ref_of_sphere(~int(v.y)));
             }
-            rtfs_smem[q_nodes + i] = v;
+            rtfs_smem[q_nodes + (i >> 2) * kStagedNodeQuads + (i & 3)] = v;
         }
         for (int i = threadIdx.x; i < n_sph_q; i += blockDim.x) rtfs_smem[q_spheres + i] = __ldg(reinterpret_cast<const uint4 *>(g.spheres) + i);
         for (int i = threadIdx.x; i < n_mat_q; i += blockDim.x) rtfs_smem[q_mats + i] = __ldg(g.mats + i);

@@ -631,7 +631,7 @@ static int plan_launch(DeviceScene *ds, FrameParams &fp, bool probe, bool count,
     // and not with the wide tree (no flow variant) nor when the bounce budget does not fit the byte it shares with the colour
     const bool flow = (fp.opt_flags & RT_FLAG_FLOW) && !(fp.opt_flags & RT_FLAG_LOCKSTEP) && !wide_asked && fp.cam.depth <= kMaxFlowDepth;
     const size_t warp_q = (kBlockThreads / 32) * (flow ? sizeof(FlowWarp) : sizeof(WarpScratch)) / 16;
-    const size_t nodes_q = size_t(ds->g.n_nodes) * 4, sph_q = size_t(ds->g.n_bounded), mat_q = size_t(ds->g.n_bounded + ds->g.n_unbounded) * 2;
+    const size_t nodes_q = size_t(ds->g.n_nodes) * kStagedNodeQuads, sph_q = size_t(ds->g.n_bounded), mat_q = size_t(ds->g.n_bounded + ds->g.n_unbounded) * 2;
     const size_t scene_q = nodes_q + sph_q + mat_q;
     // stage the scene in shared memory when it fits beside the per-warp scratch (one block per SM)
     bool smem = (scene_q + warp_q) * 16 + 1024 <= ds->ws->smem_optin && ds->g.n_bounded > 0;

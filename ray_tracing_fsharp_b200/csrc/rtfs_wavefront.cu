@@ -243,7 +243,7 @@ int render_wavefront(RtScene *scene, const RtCamera *camera, int32_t max_w, int3
 
     // shared-memory staging plan (persistent grid-stride blocks)
     const bool no_smem = (opts->flags & RT_FLAG_NO_SMEM) != 0;
-    const size_t nodes_q = size_t(ds->g.n_nodes) * 4, sph_q = size_t(ds->g.n_bounded), mat_q = size_t(ds->g.n_bounded + ds->g.n_unbounded) * 2;
+    const size_t nodes_q = size_t(ds->g.n_nodes) * kStagedNodeQuads, sph_q = size_t(ds->g.n_bounded), mat_q = size_t(ds->g.n_bounded + ds->g.n_unbounded) * 2;
     const size_t scene_bytes = (nodes_q + sph_q + mat_q) * 16;
     const bool smem = !no_smem && ds->g.n_bounded > 0 && scene_bytes * 2 + 2048 <= ws->smem_optin; // two blocks per SM
     const size_t smem_bytes = smem ? scene_bytes : 0;
