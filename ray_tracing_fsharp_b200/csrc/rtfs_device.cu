@@ -333,11 +333,8 @@ struct ItemSlot {
     int gpix[32];  // row * cols + col of the same pixels, -1: none
     int acc[3][32];
 };
-constexpr int kItemSlots = 4;
-struct WarpScratch {
-    ItemSlot slot[kItemSlots];
-};
-static_assert(sizeof(WarpScratch) % 16 == 0, "WarpScratch must be a multiple of 16 bytes");
+static_assert(sizeof(ItemSlot) % 16 == 0, "ItemSlot must be a multiple of 16 bytes");
+constexpr size_t warp_scratch_bytes(bool staged) { return size_t(item_slots(staged)) * sizeof(ItemSlot); } // per warp
 
 __device__ __forceinline__ void flush_counters(unsigned long long *counters, uint32_t paths, uint32_t rays, TraversalCounters cn, bool count) {
     for (int off = 16; off > 0; off >>= 1) {
@@ -370,7 +367,7 @@ __device__ __forceinline__ void flush_counters(unsigned long long *counters, uin
 // A warp issues one instruction every ~7.6 cycles whatever the load, so the kernel ends one whole item after the
 // work runs out: hence chunks of decreasing length, the last ones a single sample (see build_chunks).
 template <bool PROBE, bool SMEM, bool COUNT, bool SSTACK, bool WIDE>
-__global__ void __launch_bounds__(kBlockThreads, 1) render_kernel(const FrameParams fp) {
+__global__ void __launch_bounds__(block_threads(SMEM), blocks_per_sm(SMEM)) render_kernel(const FrameParams fp) {
     const SceneAccess<SMEM> sc = stage_scene<SMEM>(fp);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     typename std::conditional<SSTACK, SharedStack, LocalStack>::type stack;
@@ -379,7 +376,8 @@ __global__ void __launch_bounds__(kBlockThreads, 1) render_kernel(const FramePar
         stack.stride = 4u * blockDim.x; // words of one stack level (wide walk: two levels per entry)
         stack.levels = fp.stack_levels;
     }
-    WarpScratch *ws = reinterpret_cast<WarpScratch *>(rtfs_smem + fp.s_warp) + warp;
+    constexpr int kSlots = SMEM ? kItemSlots : kGlobalItemSlots;
+    ItemSlot *const slots = reinterpret_cast<ItemSlot *>(rtfs_smem + fp.s_warp) + warp * kSlots; // this warp's item slots
     unsigned long long *work = fp.counters + (PROBE ? CN_WORK_PROBE : CN_WORK_MAIN);
     uint32_t n_paths = 0, n_rays = 0;
     TraversalCounters cn{0, 0};
@@ -444,15 +442,15 @@ __global__ void __launch_bounds__(kBlockThreads, 1) render_kernel(const FramePar
         unsigned holds = 1u; // slots that hold an item not yet flushed
         bool finishing = false;
         int n_entries;
-        int pool = load_item(&ws->slot[0], item, n_entries);
-        int j_begin = ws->slot[0].j_begin;
+        int pool = load_item(&slots[0], item, n_entries);
+        int j_begin = slots[0].j_begin;
         unsigned long long prefetched = fetch_item();
         PathState ps;
         bool active = false, dry = false;
         int lane_slot = 0, my = 0; // my: slot index of this lane's path; lane_slot: its pixel within the item
         for (;;) {
             if (!active && !dry) {
-                ItemSlot *sl = &ws->slot[cur];
+                ItemSlot *sl = &slots[cur];
                 int q = atomicAdd(&sl->cursor, 1);
                 if (q >= pool) {
                     dry = true;
@@ -476,11 +474,11 @@ __global__ void __launch_bounds__(kBlockThreads, 1) render_kernel(const FramePar
                 if (!finishing) {
                     int free_slot = -1;
 #pragma unroll
-                    for (int sidx = 0; sidx < kItemSlots; ++sidx) {
+                    for (int sidx = 0; sidx < kSlots; ++sidx) {
                         if (sidx == cur) continue;
                         if ((holds >> sidx) & 1u) {
                             if (__any_sync(0xffffffffu, active && my == sidx)) continue; // stragglers
-                            flush_item(&ws->slot[sidx]);
+                            flush_item(&slots[sidx]);
                             holds &= ~(1u << sidx);
                         }
                         if (free_slot < 0) free_slot = sidx;
@@ -488,7 +486,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) render_kernel(const FramePar
                     if (free_slot >= 0) {
                         item = __shfl_sync(0xffffffffu, prefetched, 0);
                         if (item < n_items) {
-                            ItemSlot *next = &ws->slot[free_slot];
+                            ItemSlot *next = &slots[free_slot];
                             pool = load_item(next, item, n_entries);
                             j_begin = next->j_begin;
                             prefetched = fetch_item();
@@ -507,8 +505,8 @@ __global__ void __launch_bounds__(kBlockThreads, 1) render_kernel(const FramePar
                 uint32_t result;
                 ++n_rays;
                 if (path_step<SMEM, COUNT, decltype(stack), WIDE>(ps, sc, fp.cam.depth, result, cn, tracing, stack)) {
-                    RTFS_BOUNDS(my >= 0 && my < kItemSlots && lane_slot >= 0 && lane_slot < 32);
-                    int *acc = &ws->slot[my].acc[0][0]; // PixelStats.add into the item's accumulators
+                    RTFS_BOUNDS(my >= 0 && my < kSlots && lane_slot >= 0 && lane_slot < 32);
+                    int *acc = &slots[my].acc[0][0]; // PixelStats.add into the item's accumulators
                     atomicAdd(acc + lane_slot, int((result >> 16) & 255u));
                     atomicAdd(acc + 32 + lane_slot, int((result >> 8) & 255u));
                     atomicAdd(acc + 64 + lane_slot, int(result & 255u));
@@ -517,8 +515,8 @@ __global__ void __launch_bounds__(kBlockThreads, 1) render_kernel(const FramePar
                 }
             }
         }
-        for (int sidx = 0; sidx < kItemSlots; ++sidx) // no path is in flight any more
-            if ((holds >> sidx) & 1u) flush_item(&ws->slot[sidx]);
+        for (int sidx = 0; sidx < kSlots; ++sidx) // no path is in flight any more
+            if ((holds >> sidx) & 1u) flush_item(&slots[sidx]);
     }
     flush_counters(fp.counters, n_paths, n_rays, cn, COUNT);
 }
@@ -601,7 +599,7 @@ int check_frame_args(const RtScene *scene, const RtCamera *camera, int max_w, in
 struct LaunchPlan {
     bool smem;
     size_t smem_bytes;
-    int blocks;
+    int blocks, threads;
 };
 
 typedef void (*RenderKernelFn)(const FrameParams);
@@ -624,19 +622,28 @@ static RenderKernelFn pick_kernel(bool probe, bool smem, bool count, bool sstack
     return smem ? pick_count<false, true, false, false>(count) : pick_global<false>(sstack, wide, count);
 }
 
+// does a block with `bytes` of dynamic shared memory leave room for `per_sm` of its kind on an SM (1 KB reserved per block)
+static bool smem_fits(const DeviceScene *ds, size_t bytes, int per_sm) {
+    return (bytes + 1024) * size_t(per_sm) <= ds->ws->smem_optin + (per_sm > 1 ? 1024 : 0);
+}
+
 // lays out shared memory and sizes the persistent grid
 static int plan_launch(DeviceScene *ds, FrameParams &fp, bool probe, bool count, bool no_smem, LaunchPlan &plan, RenderKernelFn &fn) {
     const bool wide_asked = frame_walks_wide_tree(ds, fp.opt_flags, true);
     // the flow schedule (ring of rays per warp) on request only — measured slower than lockstep on B200 —
     // and not with the wide tree (no flow variant) nor when the bounce budget does not fit the byte it shares with the colour
     const bool flow = (fp.opt_flags & RT_FLAG_FLOW) && !(fp.opt_flags & RT_FLAG_LOCKSTEP) && !wide_asked && fp.cam.depth <= kMaxFlowDepth;
-    const size_t warp_q = (kBlockThreads / 32) * (flow ? sizeof(FlowWarp) : sizeof(WarpScratch)) / 16;
+    size_t warp_q = (kBlockThreads / 32) * (flow ? sizeof(FlowWarp) : warp_scratch_bytes(true)) / 16;
     const size_t nodes_q = size_t(ds->g.n_nodes) * kStagedNodeQuads, sph_q = size_t(ds->g.n_bounded), mat_q = size_t(ds->g.n_bounded + ds->g.n_unbounded) * 2;
     const size_t scene_q = nodes_q + sph_q + mat_q;
     // stage the scene in shared memory when it fits beside the per-warp scratch (one block per SM)
-    bool smem = (scene_q + warp_q) * 16 + 1024 <= ds->ws->smem_optin && ds->g.n_bounded > 0;
+    bool smem = smem_fits(ds, (scene_q + warp_q) * 16, kBlocksPerSm) && ds->g.n_bounded > 0;
     const bool wide = frame_walks_wide_tree(ds, fp.opt_flags, smem);
     if (no_smem || wide) smem = false;
+    // the launch shape follows from where the scene is read (rtfs_device.h); the flow kernels keep one block of 1024
+    plan.threads = flow ? kBlockThreads : block_threads(smem);
+    const int want_per_sm = flow ? 1 : blocks_per_sm(smem);
+    warp_q = size_t(plan.threads / 32) * (flow ? sizeof(FlowWarp) : warp_scratch_bytes(smem)) / 16;
     fp.s_nodes = 0;
     fp.s_spheres = uint32_t(nodes_q);
     fp.s_mats = uint32_t(nodes_q + sph_q);
@@ -646,8 +653,8 @@ static int plan_launch(DeviceScene *ds, FrameParams &fp, bool probe, bool count,
     // (measured on the 100 k-sphere scene at 16 spp: 124.3 against 128.2 ms; with the scene itself in shared memory the
     // same change is within noise, 67.1 against 67.4 ms on C2, 137.7 against 136.7 on C4, so those kernels keep a local stack)
     const size_t used_q = (smem ? scene_q : 0) + warp_q;
-    const size_t stack_q = size_t(wide ? 2 * (ds->wide_depth + 1) : ds->max_depth + 1) * kBlockThreads * 4 / 16;
-    const bool sstack = !flow && !smem && ds->g.n_bounded > 0 && (used_q + stack_q) * 16 + 1024 <= ds->ws->smem_optin;
+    const size_t stack_q = size_t(wide ? 2 * (ds->wide_depth + 1) : ds->max_depth + 1) * size_t(plan.threads) * 4 / 16;
+    const bool sstack = !flow && !smem && ds->g.n_bounded > 0 && smem_fits(ds, (used_q + stack_q) * 16, want_per_sm);
     fp.s_stack = uint32_t(used_q);
     {
         static const int forced = [] {
@@ -656,7 +663,7 @@ static int plan_launch(DeviceScene *ds, FrameParams &fp, bool probe, bool count,
         }();
         fp.quantum = forced ? forced : (smem ? kFlowQuantumSmall : kFlowQuantumBig);
     }
-    fp.stack_levels = int32_t(stack_q * 16 / (kBlockThreads * 4));
+    fp.stack_levels = int32_t(stack_q * 16 / (size_t(plan.threads) * 4));
     plan.smem_bytes = (used_q + (sstack ? stack_q : 0)) * 16;
     fn = flow ? (probe ? pick_flow<true>(smem, count) : pick_flow<false>(smem, count)) : pick_kernel(probe, smem, count, sstack, wide);
     { // The dynamic shared-memory limit of a kernel is a per-function, per-device setting: it is only ever RAISED here
@@ -682,7 +689,7 @@ static int plan_launch(DeviceScene *ds, FrameParams &fp, bool probe, bool count,
         for (const Known &k : known)
             if (k.fn == (const void *)fn && k.smem == plan.smem_bytes && k.device == ds->device) per_sm = k.per_sm;
         if (per_sm < 0) {
-            RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)fn, kBlockThreads, plan.smem_bytes));
+            RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)fn, plan.threads, plan.smem_bytes));
             known.push_back(Known{(const void *)fn, plan.smem_bytes, ds->device, per_sm});
         }
         if (per_sm < 1) return fail(RT_ERR_CUDA, "render kernel does not fit on an SM");
@@ -794,9 +801,9 @@ int launch_probe(DeviceScene *ds, FrameParams fp, bool count, bool no_smem, cuda
     int rc = plan_launch(ds, fp, true, count, no_smem, plan, fn);
     if (rc != RT_OK) return rc;
     const size_t n_units = size_t((fp.tiles_x * fp.tiles_y - fp.rank + fp.world - 1) / fp.world);
-    rc = build_chunks(fp, fp.n_probe, fp.first_trial + 1, n_units, plan.blocks * (kBlockThreads / 32));
+    rc = build_chunks(fp, fp.n_probe, fp.first_trial + 1, n_units, plan.blocks * (plan.threads / 32));
     if (rc != RT_OK) return rc;
-    fn<<<plan.blocks, kBlockThreads, plan.smem_bytes, st>>>(fp);
+    fn<<<plan.blocks, plan.threads, plan.smem_bytes, st>>>(fp);
     RT_CUDA(cudaGetLastError());
     ++*launches;
     probe_flags_kernel<<<unsigned((n_pixels + 255) / 256), 256, 0, st>>>(fp.stats, ws->d_stats_b, fp.flags, fp.cam.rows, fp.cam.cols, fp.tiles_x,
@@ -824,10 +831,10 @@ int launch_main(DeviceScene *ds, FrameParams fp, const FlagsView &flags, bool co
     int n_span = fp.sample_end - fp.sample_begin - fp.rank;
     int n_local = n_span > 0 ? (n_span + fp.world - 1) / fp.world : 0;
     // the list length is only known on the device; size the chunks for the whole frame (an upper bound on the units)
-    rc = build_chunks(fp, n_local, -1, (n_pixels + 31) / 32, plan.blocks * (kBlockThreads / 32));
+    rc = build_chunks(fp, n_local, -1, (n_pixels + 31) / 32, plan.blocks * (plan.threads / 32));
     if (rc != RT_OK) return rc;
     if (n_local > 0) {
-        fn<<<plan.blocks, kBlockThreads, plan.smem_bytes, st>>>(fp);
+        fn<<<plan.blocks, plan.threads, plan.smem_bytes, st>>>(fp);
         RT_CUDA(cudaGetLastError());
         ++*launches;
     }
@@ -885,9 +892,9 @@ int rt_device_count(void) {
 size_t rt_scene_shared_memory_bytes(const RtScene *scene) {
     if (!scene || !scene->dev) return 0;
     auto *ds = static_cast<const DeviceScene *>(scene->dev);
-    const size_t warp_q = (kBlockThreads / 32) * sizeof(WarpScratch) / 16; // the default (lockstep) schedule's per-warp scratch
-    const size_t scene_q = size_t(ds->g.n_nodes) * 4 + size_t(ds->g.n_bounded) + size_t(ds->g.n_bounded + ds->g.n_unbounded) * 2;
-    bool smem = (scene_q + warp_q) * 16 + 1024 <= ds->ws->smem_optin && ds->g.n_bounded > 0;
+    const size_t warp_q = (kBlockThreads / 32) * warp_scratch_bytes(true) / 16; // the default (lockstep) schedule's per-warp scratch
+    const size_t scene_q = size_t(ds->g.n_nodes) * kStagedNodeQuads + size_t(ds->g.n_bounded) + size_t(ds->g.n_bounded + ds->g.n_unbounded) * 2;
+    bool smem = smem_fits(ds, (scene_q + warp_q) * 16, kBlocksPerSm) && ds->g.n_bounded > 0;
     return smem ? scene_q * 16 : 0;
 }
 

@@ -85,7 +85,42 @@ struct DeviceScene {
 
 constexpr int kTileW = 8, kTileH = 4; // a warp's 32 pixels
 constexpr int kMaxChunks = 192;
-constexpr int kBlockThreads = 1024; // one persistent block per SM: 32 warps at 64 registers per thread (issue-bound kernel: more warps per scheduler pays)
+// Launch shape of the render kernels (measured on B200).
+//   scene staged in shared memory: ONE persistent block of 1024 threads per SM at 64 registers per thread.  That kernel is bound
+//     by instruction issue and its walk loop wants the registers (896 threads at 72 registers and 2 x 640 at 48 both lost);
+//   scene read from global memory / L2 (big scenes): TWO blocks of 768 threads per SM at 40 registers per thread.  That kernel
+//     waits on L2 (long-scoreboard stalls), so 48 warps per SM hide more latency than 32: 100 k spheres at 32 spp 219 -> 203 ms;
+//     the spills land outside the walk loop.  (2 x 640 at 48 registers: 211 ms; 2 x 1024 at 32: 253 ms, spills inside the loop.)
+// The macros exist for A/B builds.
+#ifndef RTFS_BLOCK_THREADS
+#define RTFS_BLOCK_THREADS 1024
+#endif
+#ifndef RTFS_BLOCKS_PER_SM
+#define RTFS_BLOCKS_PER_SM 1
+#endif
+#ifndef RTFS_GLOBAL_BLOCK_THREADS
+#define RTFS_GLOBAL_BLOCK_THREADS 768
+#endif
+#ifndef RTFS_GLOBAL_BLOCKS_PER_SM
+#define RTFS_GLOBAL_BLOCKS_PER_SM 2
+#endif
+#ifndef RTFS_ITEM_SLOTS
+#define RTFS_ITEM_SLOTS 4
+#endif
+#ifndef RTFS_GLOBAL_ITEM_SLOTS
+#define RTFS_GLOBAL_ITEM_SLOTS 3
+#endif
+constexpr int kBlockThreads = RTFS_BLOCK_THREADS;
+constexpr int kBlocksPerSm = RTFS_BLOCKS_PER_SM;
+constexpr int kGlobalBlockThreads = RTFS_GLOBAL_BLOCK_THREADS;
+constexpr int kGlobalBlocksPerSm = RTFS_GLOBAL_BLOCKS_PER_SM;
+// Work-item slots per warp (rtfs_device.cu).  Four keep a warp fed best; a scene read from global memory lives on what is left of
+// the L1 after the shared-memory carve-out, and there three slots (a 100 KB carve-out, 128 KB of L1) beat four (132 / 96 KB) by
+// 7 % and two (64 / 164 KB, but warps run dry) by 9 % on the 100 k-sphere scene.
+constexpr int kItemSlots = RTFS_ITEM_SLOTS, kGlobalItemSlots = RTFS_GLOBAL_ITEM_SLOTS;
+constexpr int item_slots(bool staged) { return staged ? kItemSlots : kGlobalItemSlots; }
+constexpr int block_threads(bool staged) { return staged ? kBlockThreads : kGlobalBlockThreads; }
+constexpr int blocks_per_sm(bool staged) { return staged ? kBlocksPerSm : kGlobalBlocksPerSm; }
 
 struct FrameParams {
     SceneGlobal g;
