@@ -323,15 +323,17 @@ __device__ __forceinline__ SceneAccess<SMEM> stage_scene(const FrameParams &fp) 
     return sc;
 }
 
-// per-warp scratch in shared memory: item slots (one being issued, the others with their last paths still in flight)
+// per-warp scratch in shared memory: item slots (one being issued, the others with their last paths still in flight).
+// 400 bytes each: for a scene read from global memory what shared memory the slots take is L1 the walk does not get.
+// A pixel's red and green sums share a word (16 bits each): a chunk is at most kMaxChunkSamples = 256 samples, 256 x 255 < 2^16.
 struct ItemSlot {
     int cursor;    // next path of the item's pool
     int j_begin;   // first local sample index of the item's chunk
     int j_len;     // samples in the chunk (also what the flush adds to the pixels' count field)
     int to_b;      // probe: the chunk belongs to the second accumulator set
     int pix[32];   // row << 16 | col of each of the 32 pixels, -1: none
-    int gpix[32];  // row * cols + col of the same pixels, -1: none
-    int acc[3][32];
+    unsigned acc_rg[32]; // sum of red | sum of green << 16
+    unsigned acc_b[32];  // sum of blue
 };
 static_assert(sizeof(ItemSlot) % 16 == 0, "ItemSlot must be a multiple of 16 bytes");
 constexpr size_t warp_scratch_bytes(bool staged) { return size_t(item_slots(staged)) * sizeof(ItemSlot); } // per warp
@@ -403,8 +405,7 @@ __global__ void __launch_bounds__(block_threads(SMEM), blocks_per_sm(SMEM)) rend
             if (e < n_list) my_pixel = int(fp.list[e]);
             n_entries = int(min(32u, n_list - unit * 32u));
         }
-        sl->acc[0][lane] = 0; sl->acc[1][lane] = 0; sl->acc[2][lane] = 0;
-        sl->gpix[lane] = my_pixel;
+        sl->acc_rg[lane] = 0u; sl->acc_b[lane] = 0u;
         sl->pix[lane] = my_pixel < 0 ? -1 : (((my_pixel / fp.cam.cols) << 16) | (my_pixel % fp.cam.cols));
         if (lane == 0) {
             sl->cursor = 0;
@@ -418,12 +419,13 @@ __global__ void __launch_bounds__(block_threads(SMEM), blocks_per_sm(SMEM)) rend
     // Retires a slot whose paths have all finished: one RED per channel and pixel (PixelStats.add, Pixel.fs:87-95)
     auto flush_item = [&](ItemSlot *sl) {
         __syncwarp();
-        int px = sl->gpix[lane];
-        if (px >= 0) {
-            int *st = (sl->to_b ? fp.stats_b : fp.stats) + 4 * size_t(px);
-            atomicAdd(st + 0, sl->acc[0][lane]);
-            atomicAdd(st + 1, sl->acc[1][lane]);
-            atomicAdd(st + 2, sl->acc[2][lane]);
+        const int rc = sl->pix[lane];
+        if (rc >= 0) {
+            int *st = (sl->to_b ? fp.stats_b : fp.stats) + 4 * (size_t(rc >> 16) * size_t(fp.cam.cols) + size_t(rc & 0xffff));
+            const unsigned rg = sl->acc_rg[lane];
+            atomicAdd(st + 0, int(rg & 0xffffu));
+            atomicAdd(st + 1, int(rg >> 16));
+            atomicAdd(st + 2, int(sl->acc_b[lane]));
             atomicAdd(st + 3, sl->j_len);
         }
         __syncwarp();
@@ -433,6 +435,7 @@ __global__ void __launch_bounds__(block_threads(SMEM), blocks_per_sm(SMEM)) rend
     };
 
     unsigned long long item = __shfl_sync(0xffffffffu, fetch_item(), 0);
+    if (threadIdx.x == 0 && item < n_items) atomicAdd(fp.counters + CN_BUSY_BLOCKS, 1ull); // blocks that found work: the resident ones
     if (item < n_items) {
         // kItemSlots slots per warp: lanes pull paths from slot `cur`; when its pool is dry the next item is loaded into a
         // free slot straight away, so lanes do not idle while the last paths of an item complete.  A slot is free once
@@ -506,10 +509,9 @@ __global__ void __launch_bounds__(block_threads(SMEM), blocks_per_sm(SMEM)) rend
                 ++n_rays;
                 if (path_step<SMEM, COUNT, decltype(stack), WIDE>(ps, sc, fp.cam.depth, result, cn, tracing, stack)) {
                     RTFS_BOUNDS(my >= 0 && my < kSlots && lane_slot >= 0 && lane_slot < 32);
-                    int *acc = &slots[my].acc[0][0]; // PixelStats.add into the item's accumulators
-                    atomicAdd(acc + lane_slot, int((result >> 16) & 255u));
-                    atomicAdd(acc + 32 + lane_slot, int((result >> 8) & 255u));
-                    atomicAdd(acc + 64 + lane_slot, int(result & 255u));
+                    ItemSlot *mine = &slots[my]; // PixelStats.add into the item's accumulators
+                    atomicAdd(&mine->acc_rg[lane_slot], ((result >> 16) & 255u) | ((result << 8) & 0x00ff0000u));
+                    atomicAdd(&mine->acc_b[lane_slot], result & 255u);
                     if (result & kDegenerate) atomicAdd(fp.counters + CN_DEGENERATE, 1ull);
                     active = false;
                 }
@@ -682,6 +684,11 @@ static int plan_launch(DeviceScene *ds, FrameParams &fp, bool probe, bool count,
             if (k.fn == (const void *)fn && k.device == ds->device) limit = &k;
         if (!limit || limit->smem < plan.smem_bytes) {
             RT_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(plan.smem_bytes)));
+            // Two blocks per SM must both be resident (a persistent kernel's second wave finds no work left).  The occupancy
+            // query below answers 2 whenever the SM COULD hold them, but the carve-out the driver picks by default at launch
+            // is not always large enough for both (measured: with 61 KB of dynamic shared memory per block only 148 of the 296
+            // blocks ever ran, 100 k spheres 279 ms instead of 202), so the largest carve-out is asked for explicitly.
+            if (!smem && !flow) RT_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             if (limit) limit->smem = plan.smem_bytes;
             else limits.push_back(Known{(const void *)fn, plan.smem_bytes, ds->device, 0});
         }
@@ -744,7 +751,7 @@ static int build_chunks(FrameParams &fp, int n_local, int boundary, size_t n_uni
     // bulk chunk: every warp should see ~16 bulk items; at most 32 samples (1024 paths) per item
     long long bulk = (long long)(n_units * size_t(n_local)) / (16LL * std::max(1, resident_warps));
     bulk = std::max(1LL, std::min(32LL, bulk));
-    bulk = std::max(bulk, (long long)((n_local + 159) / 160)); // the table has kMaxChunks entries
+    bulk = std::max(bulk, (long long)((n_local + 159) / 160)); // the table has kMaxChunks entries; n_local <= kMaxLaunchSamples keeps bulk <= kMaxChunkSamples
     std::vector<int> sizes;
     for (int t = int(bulk) / 2; t >= 1; t /= 2) sizes.push_back(t);
     if (bulk > 1) sizes.push_back(1);
@@ -831,9 +838,13 @@ int launch_main(DeviceScene *ds, FrameParams fp, const FlagsView &flags, bool co
     int n_span = fp.sample_end - fp.sample_begin - fp.rank;
     int n_local = n_span > 0 ? (n_span + fp.world - 1) / fp.world : 0;
     // the list length is only known on the device; size the chunks for the whole frame (an upper bound on the units)
-    rc = build_chunks(fp, n_local, -1, (n_pixels + 31) / 32, plan.blocks * (plan.threads / 32));
-    if (rc != RT_OK) return rc;
-    if (n_local > 0) {
+    // one launch covers at most kMaxLaunchSamples of this rank's sample indices (a chunk stays within kMaxChunkSamples: the
+    // 16-bit halves of an item's red | green word); a frame with more is several launches
+    for (int base = 0; base < n_local; base += kMaxLaunchSamples) {
+        rc = build_chunks(fp, std::min(kMaxLaunchSamples, n_local - base), -1, (n_pixels + 31) / 32, plan.blocks * (plan.threads / 32));
+        if (rc != RT_OK) return rc;
+        for (int k = 0; k < fp.n_chunks; ++k) fp.chunk_begin[k] += uint32_t(base);
+        if (base > 0) RT_CUDA(cudaMemsetAsync(ds->ws->d_counters + CN_WORK_MAIN, 0, sizeof(unsigned long long), st));
         fn<<<plan.blocks, plan.threads, plan.smem_bytes, st>>>(fp);
         RT_CUDA(cudaGetLastError());
         ++*launches;
@@ -848,6 +859,7 @@ void read_counters(DeviceScene *ds, RtStats *stats, size_t n_pixels, bool adapti
     stats->prim_tests = ds->ws->h_counters[CN_PRIM];
     stats->pixels_early_out = adaptive ? (unsigned long long)n_pixels - ds->ws->h_counters[CN_LIST] : 0;
     stats->degenerate_paths = ds->ws->h_counters[CN_DEGENERATE];
+    if (std::getenv("RTFS_DEBUG_BLOCKS")) std::fprintf(stderr, "rtfs: blocks that found work (probe + main): %llu\n", ds->ws->h_counters[CN_BUSY_BLOCKS]);
 }
 
 // implemented in rtfs_wavefront.cu

@@ -32,7 +32,7 @@ inline int require_device(int device) {
 // ---------------------------------------------------------------------------------------------------
 // device scene
 // ---------------------------------------------------------------------------------------------------
-enum CounterSlot { CN_PATHS = 0, CN_RAYS = 1, CN_BOX = 2, CN_PRIM = 3, CN_LIST = 4, CN_WORK_PROBE = 5, CN_WORK_MAIN = 6, CN_DEGENERATE = 7, CN_SLOTS = 16 };
+enum CounterSlot { CN_PATHS = 0, CN_RAYS = 1, CN_BOX = 2, CN_PRIM = 3, CN_LIST = 4, CN_WORK_PROBE = 5, CN_WORK_MAIN = 6, CN_DEGENERATE = 7, CN_BUSY_BLOCKS = 8, CN_SLOTS = 16 };
 // (the last slot of the pinned copy is a scratch word of the wavefront driver; the pinned buffer holds a second set of
 // CN_SLOTS words: the snapshot taken between the probe and the main phase)
 
@@ -85,6 +85,8 @@ struct DeviceScene {
 
 constexpr int kTileW = 8, kTileH = 4; // a warp's 32 pixels
 constexpr int kMaxChunks = 192;
+constexpr int kMaxChunkSamples = 256;                    // samples of one pixel in a work item (16-bit colour sums: 256 x 255 < 2^16)
+constexpr int kMaxLaunchSamples = 160 * kMaxChunkSamples; // sample indices of one rank a single main-phase launch covers (build_chunks)
 // Launch shape of the render kernels (measured on B200).
 //   scene staged in shared memory: ONE persistent block of 1024 threads per SM at 64 registers per thread.  That kernel is bound
 //     by instruction issue and its walk loop wants the registers (896 threads at 72 registers and 2 x 640 at 48 both lost);
@@ -108,15 +110,14 @@ constexpr int kMaxChunks = 192;
 #define RTFS_ITEM_SLOTS 4
 #endif
 #ifndef RTFS_GLOBAL_ITEM_SLOTS
-#define RTFS_GLOBAL_ITEM_SLOTS 3
+#define RTFS_GLOBAL_ITEM_SLOTS 4
 #endif
 constexpr int kBlockThreads = RTFS_BLOCK_THREADS;
 constexpr int kBlocksPerSm = RTFS_BLOCKS_PER_SM;
 constexpr int kGlobalBlockThreads = RTFS_GLOBAL_BLOCK_THREADS;
 constexpr int kGlobalBlocksPerSm = RTFS_GLOBAL_BLOCKS_PER_SM;
-// Work-item slots per warp (rtfs_device.cu).  Four keep a warp fed best; a scene read from global memory lives on what is left of
-// the L1 after the shared-memory carve-out, and there three slots (a 100 KB carve-out, 128 KB of L1) beat four (132 / 96 KB) by
-// 7 % and two (64 / 164 KB, but warps run dry) by 9 % on the 100 k-sphere scene.
+// Work-item slots per warp (rtfs_device.cu, 400 bytes each).  Four keep a warp fed best: on the 100 k-sphere scene (two blocks of
+// 768 threads per SM) four slots 199.5 ms, three 202, two 222 (warps run dry).
 constexpr int kItemSlots = RTFS_ITEM_SLOTS, kGlobalItemSlots = RTFS_GLOBAL_ITEM_SLOTS;
 constexpr int item_slots(bool staged) { return staged ? kItemSlots : kGlobalItemSlots; }
 constexpr int block_threads(bool staged) { return staged ? kBlockThreads : kGlobalBlockThreads; }

@@ -199,6 +199,23 @@ def test_flow_and_lockstep_schedules_agree_bit_for_bit(which):
         assert np.array_equal(s1, s2), (which, spp)
 
 
+def test_more_samples_than_one_main_launch_covers():
+    """A work item holds at most 256 samples of a pixel (its red and green sums share a word) and one main-phase launch at
+    most 160 x 256 sample indices of a rank: a frame with more is several launches.  3 x 3 pixels at 41 500 spp (adaptive off
+    and on), against the flow kernel (accumulators of its own, one launch) and against the known totals."""
+    spec = _small("C1", 1, 1, 41500)
+    osc, dsc, cam = scene_pair(spec)
+    for adaptive in (False, True):
+        _, s1, st1 = dsc.render(cam, 1, 1, seed=5, adaptive=adaptive, want_sums=True)
+        s1 = s1.copy()
+        _, s2, st2 = dsc.render(cam, 1, 1, seed=5, adaptive=adaptive, want_sums=True, flags=abi.RT_FLAG_FLOW)
+        assert np.array_equal(s1, s2) and int(st1.paths) == int(st2.paths) and int(st1.rays) == int(st2.rays)
+        assert set(np.unique(s1[..., 3]).tolist()) <= {11, 41500}
+        if not adaptive:
+            assert (s1[..., 3] == 41500).all() and int(st1.paths) == 9 * 41500
+        assert (s1[..., :3] <= 255 * s1[..., 3:4]).all() and (s1[..., :3] >= 0).all()
+
+
 def test_stats_of_a_frame_and_page_locked_output_frames():
     """RtStats of rt_render (the main-phase kernel's own time and rays, no degenerate paths on a well-formed scene), and
     native.FrameRing: explicitly recycled, page-locked output arrays (rt_host_pin) receive the same frame as a fresh one."""
