@@ -202,6 +202,12 @@ int rt_scene_bvh_nodes(const RtScene *scene, int32_t which, double *bounds, int3
  * lies below it (RT_ERR_DEGENERATE otherwise).  Outputs are optional. */
 int rt_scene_wide_bvh_check(RtScene *scene, int32_t *n_nodes, int32_t *depth, int32_t *n_spheres,
                             double *mean_children);
+/* The tree as the render kernels read it (binary SAH tree, child boxes as centre / half-extent with the left and right child's
+ * values side by side for the packed FP32 slab test; replaces BoundingBoxTree.fs:9-43 / Scene.fs:30-60): verifies on the host
+ * that no converted box is smaller than the box it was made from, that every bounded sphere of non-negative radius is the leaf
+ * of exactly one node and lies inside that leaf's box, and that the tree is no deeper than the walk stacks assume
+ * (RT_ERR_DEGENERATE otherwise).  Outputs are optional. */
+int rt_scene_device_bvh_check(RtScene *scene, int32_t *n_nodes, int32_t *depth, int32_t *n_spheres);
 /* bytes of scene data resident on the device (nodes + primitives + materials + textures) */
 size_t rt_scene_device_bytes(const RtScene *scene);
 /* bytes of BVH + spheres + materials that every persistent block stages in shared memory; 0 when the scene

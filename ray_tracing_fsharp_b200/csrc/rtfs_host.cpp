@@ -1037,4 +1037,63 @@ int rt_scene_wide_bvh_check(RtScene *scene, int32_t *n_nodes, int32_t *depth, in
     return RT_OK;
 }
 
+// Checks the nodes as the DEVICE will read them (device_node_of: centre / half-extent boxes, left and right child side by
+// side): every decoded box c -+ h contains the min / max box it was made from (so also every sphere below it), h >= 0, the
+// child refs are untouched, every bounded sphere is the leaf of exactly one node, and the tree is as deep as max_depth says
+// (the render kernels size their walk stacks from it).
+int rt_scene_device_bvh_check(RtScene *scene, int32_t *n_nodes, int32_t *depth, int32_t *n_spheres) {
+    if (!scene) return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_device_bvh_check: null scene");
+    const HostSceneLayout &L = scene->layout;
+    std::vector<int> seen(size_t(L.n_bounded), 0);
+    int deepest = 0;
+    struct Item {
+        int32_t ref;
+        int depth;
+    };
+    std::vector<Item> todo;
+    if (L.n_bounded > 0) todo.push_back(Item{0, 1});
+    size_t visited = 0;
+    while (!todo.empty()) {
+        const Item it = todo.back();
+        todo.pop_back();
+        if (it.ref < 0 || size_t(it.ref) >= L.nodes.size()) return fail(RT_ERR_DEGENERATE, "device BVH: child index out of range");
+        if (++visited > L.nodes.size()) return fail(RT_ERR_DEGENERATE, "device BVH: a node is reachable twice");
+        deepest = std::max(deepest, it.depth);
+        const DNode &src = L.nodes[size_t(it.ref)];
+        const DNode dev = device_node_of(src);
+        const float *q = dev.l_mn; // the twelve box floats in device order
+        if (dev.left != src.left || dev.right != src.right) return fail(RT_ERR_DEGENERATE, "device BVH: child refs changed by the conversion");
+        for (int side = 0; side < 2; ++side) {
+            if (L.root_is_leaf && it.ref == 0 && side == 1) continue; // the never-entered dummy of a one-sphere tree
+            const float *mn = side ? src.r_mn : src.l_mn, *mx = side ? src.r_mx : src.l_mx;
+            for (int a = 0; a < 3; ++a) {
+                const double c = q[2 * a + side], h = q[6 + 2 * a + side];
+                if (!(h >= 0.0) || !(c - h <= double(mn[a])) || !(c + h >= double(mx[a])))
+                    return fail(RT_ERR_DEGENERATE, "device BVH: a centre / half-extent box is smaller than the box it was made from");
+            }
+            const int32_t child = side ? src.right : src.left;
+            if (child >= 0) {
+                todo.push_back(Item{child, it.depth + 1});
+                continue;
+            }
+            const int32_t k = ~child;
+            if (k < 0 || k >= L.n_bounded) return fail(RT_ERR_DEGENERATE, "device BVH: leaf sphere index out of range");
+            ++seen[size_t(k)];
+            const DSphere &sp = L.spheres[size_t(k)];
+            const float cs[3] = {sp.cx, sp.cy, sp.cz};
+            for (int a = 0; a < 3; ++a) {
+                const double c = q[2 * a + side], h = q[6 + 2 * a + side], r = std::fabs(double(sp.r));
+                if (!(c - h <= double(cs[a]) - r) || !(c + h >= double(cs[a]) + r)) return fail(RT_ERR_DEGENERATE, "device BVH: a leaf box does not contain its sphere");
+            }
+        }
+    }
+    for (int v : seen)
+        if (v != 1) return fail(RT_ERR_DEGENERATE, "device BVH: a sphere is missing or duplicated");
+    if (L.n_bounded > 0 && deepest > L.max_depth) return fail(RT_ERR_DEGENERATE, "device BVH: deeper than max_depth (the walk stacks are sized from it)");
+    if (n_nodes) *n_nodes = int32_t(L.nodes.size());
+    if (depth) *depth = deepest;
+    if (n_spheres) *n_spheres = L.n_bounded;
+    return RT_OK;
+}
+
 } // extern "C"

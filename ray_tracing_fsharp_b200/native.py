@@ -44,6 +44,7 @@ def _declare(lib):
         "rt_scene_bvh_node_count": (C.c_int, [_vp, _i32]),
         "rt_scene_bvh_nodes": (C.c_int, [_vp, _i32, _vp, _vp, _vp]),
         "rt_scene_wide_bvh_check": (C.c_int, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(C.c_double)]),
+        "rt_scene_device_bvh_check": (C.c_int, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
         "rt_scene_device_bytes": (C.c_size_t, [_vp]),
         "rt_scene_shared_memory_bytes": (C.c_size_t, [_vp]),
         "rt_render": (C.c_int, [_vp, C.POINTER(RtCamera), _i32, _i32, C.POINTER(RtRenderOpts), _vp, _vp, C.POINTER(RtStats)]),
@@ -212,6 +213,12 @@ class SceneHandle:
         n, depth, ns, mc = _i32(), _i32(), _i32(), C.c_double()
         check(lib().rt_scene_wide_bvh_check(self.ptr, C.byref(n), C.byref(depth), C.byref(ns), C.byref(mc)))
         return {"nodes": n.value, "depth": depth.value, "spheres": ns.value, "mean_children": mc.value}
+
+    def device_bvh_check(self):
+        """Verifies on the host the binary tree in the form the render kernels read it; returns its figures."""
+        n, depth, ns = _i32(), _i32(), _i32()
+        check(lib().rt_scene_device_bvh_check(self.ptr, C.byref(n), C.byref(depth), C.byref(ns)))
+        return {"nodes": n.value, "depth": depth.value, "spheres": ns.value}
 
     def device_bytes(self):
         return int(lib().rt_scene_device_bytes(self.ptr))

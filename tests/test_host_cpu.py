@@ -164,6 +164,28 @@ def test_wide_bvh_is_valid_on_the_host(which):
     assert again == info
 
 
+@pytest.mark.parametrize("which", ["reduced", "C1", "C2", "C3", "C4", "mid", "one-sphere"])
+def test_device_bvh_is_valid_on_the_host(which):
+    """rt_scene_device_bvh_check: the binary tree as the render kernels read it (centre / half-extent boxes, the two children's
+    values side by side for the packed slab test): no converted box is smaller than the box it was made from, every bounded
+    sphere of non-negative radius is the leaf of exactly one node and inside that leaf's box, depth within the walk stacks."""
+    if which == "reduced":
+        spec = small_random_spheres()
+    elif which == "mid":
+        spec = sample_images.many_spheres(n=3000)
+    elif which == "one-sphere":
+        spec = sample_images.CONFIGS["C3"]()
+    else:
+        spec = sample_images.CONFIGS[which]()
+    hs, ts, keep = marshal(spec.objects)
+    h = native.SceneHandle(hs, ts, -1, keepalive=keep)
+    info = h.device_bvh_check()
+    n_spheres = sum(1 for o in spec.objects if isinstance(o, Hittable.Sphere) and o.sphere.Radius >= 0)
+    assert info["spheres"] == n_spheres
+    assert info["nodes"] == max(1, n_spheres - 1) if n_spheres else info["nodes"] == 0
+    assert (info["depth"] <= 64) and (info["depth"] >= 1 if n_spheres else info["depth"] == 0)
+
+
 def test_scene_create_validates_like_the_type_system_would():
     lib = native.lib()
 
