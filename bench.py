@@ -396,7 +396,7 @@ def run_ours(args):
     r = Runner(args)
     torch, rank, world = r.torch, r.rank, r.world
     r.flags = ((abi.RT_FLAG_NO_SMEM if args.no_smem else 0) | {"auto": 0, "binary": abi.RT_FLAG_BVH2, "wide": abi.RT_FLAG_WIDE_BVH}[args.bvh]
-               | (abi.RT_FLAG_FLOW if args.schedule == "flow" else 0))
+               | (abi.RT_FLAG_FLOW if args.schedule == "flow" else 0) | (abi.RT_FLAG_NO_LEAN if args.no_lean else 0))
     spec = build_spec(args)
     handle, cam = r.scene(spec)
     fp32_peak = native.measure_fp32_peak(r.local_rank) if rank == 0 else 0.0
@@ -539,6 +539,7 @@ def main():
     ap.add_argument("--half-extents", type=int, nargs=2, default=None, help="override maxWidthCoord maxHeightCoord")
     ap.add_argument("--no-adaptive", action="store_true")
     ap.add_argument("--no-smem", action="store_true")
+    ap.add_argument("--no-lean", action="store_true", help="A/B: do not use the kernel specialised for scenes without FP64 objects and texture lookups")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--bvh", default="auto", choices=["auto", "binary", "wide"],
                     help="which tree the kernels walk: auto = binary in shared memory when the scene fits, else 8-wide compressed (A/B runs)")

@@ -136,6 +136,8 @@ typedef struct RtRenderOpts {
 #define RT_FLAG_FLOW 32     /* the flow schedule: every warp keeps a ring of 64 rays in shared memory, lanes pull walks
                               from it in quanta, scatters run in full-width passes.  Bit-identical frames; measured
                               slower than lockstep on B200, kept selectable                          */
+#define RT_FLAG_NO_LEAN 64  /* do not pick the kernel specialised for scenes without FP64 unbounded objects and without
+                              texture lookups even where the scene allows it (A/B tests; frames are bit-identical)      */
 
 typedef struct RtStats {
     uint64_t paths;     /* traceOnce calls (Scene.fs:118)                                        */

@@ -43,6 +43,7 @@ RT_FLAG_WIDE_BVH = 4
 RT_FLAG_BVH2 = 8
 RT_FLAG_LOCKSTEP = 16
 RT_FLAG_FLOW = 32
+RT_FLAG_NO_LEAN = 64
 
 RT_COMM_ID_BYTES = 128
 

@@ -465,8 +465,13 @@ RTFS_HD float4 ldg_sphere(const float4 *p) {
 // ways within every quarter-warp (ncu: 39 % of all shared-memory wavefronts were bank conflicts).  At 80 bytes quad q of node
 // i starts at bank group (5 i + q) mod 8: every group equally likely.  Child refs are byte addresses, so a visit pays nothing.
 constexpr uint32_t kStagedNodeQuads = 5;
-template <bool SMEM>
+// SMEM: 0 = the scene is read from global memory, 1 = from the copy staged in shared memory, 2 = staged and LEAN: the host has
+// seen that every unbounded object is cleared for FP32 and no material has a texture index (DeviceScene::lean), so the FP64
+// evaluations of unbounded objects and the texture lookup are compiled out of that kernel (fewer instructions per ray — the
+// compiler hoists the FP64 conversions of the ray out of the loop over the objects, for every ray — and a smaller kernel).
+template <int SMEM>
 struct SceneAccess {
+    static constexpr bool kLean = SMEM == 2;
     SceneGlobal g;
     uint32_t s_nodes, s_spheres, s_mats; // SMEM only: byte addresses of the staged copies in the shared window
     // one 64-byte node: four LDS.128 from the staged copy, or two 256-bit read-only loads from global memory
@@ -622,7 +627,7 @@ struct SharedStack {
 // One visit of the walk over the tree: `node` is an internal node (>= 0: test both children's boxes, descend into
 // the nearer one, push the other) or a leaf (~k: test sphere k, pop).  Returns true when the walk is over.
 // `node`, `last_ref`, `best` and the stack entries are refs (SceneAccess); best >= 0 (kNoRef): nothing hit yet.
-template <bool SMEM, bool COUNT, class Stack>
+template <int SMEM, bool COUNT, class Stack>
 RTFS_HD bool bvh_visit(const SceneAccess<SMEM> &sc, const RaySlabs &rs, float3 o, float3 d, int last_ref, int &node, int &sp, Stack &stack,
                        float &best_t, int &best, TraversalCounters &cn) {
     if (node >= 0) {
@@ -755,13 +760,13 @@ RTFS_HD void wide_closest(const SceneGlobal &g, float3 o, float3 d, int last_ref
 
 // A path remembers the primitive its ray leaves as the walk names it: the leaf ref of a bounded sphere (< 0), the
 // device id of an unbounded object (>= n_bounded), kNoRef for a camera ray.  From a device primitive id:
-template <bool SMEM, bool WIDE = false>
+template <int SMEM, bool WIDE = false>
 RTFS_HD int ref_of_prim(const SceneAccess<SMEM> &sc, int prim) {
     if (WIDE) return prim < 0 ? kNoRef : (prim < sc.g.n_bounded ? ~sc.g.dev_to_wide[prim] : prim);
     return prim < 0 ? kNoRef : (prim < sc.g.n_bounded ? sc.ref_of_sphere(prim) : prim);
 }
 // the bounded part of hitObject: the closest sphere of the tree, if any
-template <bool SMEM, bool COUNT, class Stack>
+template <int SMEM, bool COUNT, class Stack>
 RTFS_HD void bvh_closest(const SceneAccess<SMEM> &sc, float3 o, float3 d, int last_ref, float &best_t, int &best_ref, TraversalCounters &cn,
                          Stack &stack) {
     best_t = kNoHitT;
@@ -775,7 +780,7 @@ RTFS_HD void bvh_closest(const SceneAccess<SMEM> &sc, float3 o, float3 d, int la
 }
 // the unbounded objects, after the tree (Scene.fs:77-86), and the strike point (:91)
 // (`last_ref` and `best_ref` are refs; an unbounded object's ref is its device id)
-template <bool SMEM, bool COUNT, bool WIDE = false>
+template <int SMEM, bool COUNT, bool WIDE = false>
 RTFS_HD Hit finish_hit(const SceneAccess<SMEM> &sc, float3 o, float3 d, int last_ref, float best_t, int best_ref, TraversalCounters &cn) {
     const int last = last_ref;
     int best = best_ref;
@@ -786,7 +791,7 @@ RTFS_HD Hit finish_hit(const SceneAccess<SMEM> &sc, float3 o, float3 d, int last
             float t;
             bool self = (sc.g.n_bounded + i) == last;
             bool hit;
-            if (u.fp32) { // warp-uniform: every lane is at object i
+            if (SceneAccess<SMEM>::kLean || u.fp32) { // warp-uniform: every lane is at object i
                 hit = (u.shape == RT_SHAPE_INFINITE_PLANE) ? plane_hit_big_f32(o, d, u, self, t) : sphere_hit_big_f32(o, d, af, u, self, t);
             } else {
                 const D3 od = d3(o), dd = d3(d);
@@ -812,7 +817,7 @@ RTFS_HD Hit finish_hit(const SceneAccess<SMEM> &sc, float3 o, float3 d, int last
 // full width instead of once per straggler group.
 // (Tried and dropped: parking a leaf and testing it after the walk, converged, instead of during it at ~4 active
 // lanes — the lost culling costs 5 % more slab tests and the C2 frame got 3 % slower.)
-template <bool SMEM, bool COUNT, class Stack, bool WIDE = false>
+template <int SMEM, bool COUNT, class Stack, bool WIDE = false>
 RTFS_HD Hit closest_hit_from(const SceneAccess<SMEM> &sc, float3 o, float3 d, int last_ref, TraversalCounters &cn, unsigned lanes, Stack &stack) {
     float best_t;
     int best_ref;
@@ -824,7 +829,7 @@ RTFS_HD Hit closest_hit_from(const SceneAccess<SMEM> &sc, float3 o, float3 d, in
     return finish_hit<SMEM, COUNT, WIDE>(sc, o, d, last_ref, best_t, best_ref, cn);
 }
 // the same with the ray's previous primitive given as a device primitive id (conformance entry points, wavefront)
-template <bool SMEM, bool COUNT, bool WIDE = false>
+template <int SMEM, bool COUNT, bool WIDE = false>
 RTFS_HD Hit closest_hit(const SceneAccess<SMEM> &sc, float3 o, float3 d, int last, TraversalCounters &cn, unsigned lanes) {
     LocalStack stack;
     return closest_hit_from<SMEM, COUNT, LocalStack, WIDE>(sc, o, d, ref_of_prim<SMEM, WIDE>(sc, last), cn, lanes, stack);
@@ -927,7 +932,7 @@ struct Material {
     uint32_t flags;
     int32_t host_index;
 };
-template <bool SMEM>
+template <int SMEM>
 RTFS_HD Material load_material(const SceneAccess<SMEM> &sc, int prim) {
     uint4 a = sc.mat_q(prim, 0), b = sc.mat_q(prim, 1);
     Material m;
@@ -978,7 +983,7 @@ enum ScatterResult { SCATTER_CONTINUE = 0, SCATTER_ABSORBED = 1, SCATTER_ERROR =
 // inside computation, one colour update, ONE block of the counter RNG for whichever style draws
 // (Lambert and Fuzzed: GetThree; Dielectric and Glass: Get — always the first block of the bounce), one
 // reflection, and a common "unit(base + scale * offset)" tail; only the few style-specific lines diverge.
-template <bool SMEM, class Rng>
+template <int SMEM, class Rng>
 RTFS_HD ScatterResult scatter(const SceneAccess<SMEM> &sc, int prim, int last, float3 &o, float3 &d, float3 strike, uint32_t &colour,
                               Rng &rng, bool *inside_out) {
     const Material m = load_material(sc, prim);
@@ -1002,7 +1007,7 @@ RTFS_HD ScatterResult scatter(const SceneAccess<SMEM> &sc, int prim, int last, f
             where = (prim == last) ? CMP_EQUAL : fcmp(dot(co, co), s.w * s.w);
         } else {
             const DUnbounded &u = sc.g.unb[prim - sc.g.n_bounded];
-            if (u.fp32) {
+            if (SceneAccess<SMEM>::kLean || u.fp32) {
                 // strike - C rounds at the size of the sphere (~6e-5 for r = 1000): 6e-8 of the normal's direction;
                 // inside / outside is the sign of the expanded |o - C|^2 - r^2 (Float.compare's 1e-8 band kept)
                 float3 vf = f3(strike.x - u.n[0], strike.y - u.n[1], strike.z - u.n[2]);
@@ -1029,7 +1034,7 @@ RTFS_HD ScatterResult scatter(const SceneAccess<SMEM> &sc, int prim, int last, f
 
     // ---- emitters ----
     if (style == RT_STYLE_LIGHT_SOURCE) { // Sphere.fs:185-189, InfinitePlane.fs:52-56
-        colour = combine(colour, m.texture < 0 ? m.rgb : texture_colour(sc.g, m.texture, strike));
+        colour = combine(colour, (SceneAccess<SMEM>::kLean || m.texture < 0) ? m.rgb : texture_colour(sc.g, m.texture, strike));
         return SCATTER_ABSORBED;
     }
     if (style == RT_STYLE_LIGHT_SOURCE_CAP) { // Sphere.fs:190-200; p0 = centre.x + (r - r / 4)
@@ -1039,7 +1044,7 @@ RTFS_HD ScatterResult scatter(const SceneAccess<SMEM> &sc, int prim, int last, f
     if (style > RT_STYLE_GLASS || (is_plane && style > RT_STYLE_LAMBERT_REFLECTION)) return SCATTER_ERROR;
 
     // ---- colour: darken albedo (combine incoming texture), Sphere.fs:203-207 etc., InfinitePlane.fs:40-41 ----
-    const uint32_t surface = (is_plane || m.texture < 0) ? m.rgb : texture_colour(sc.g, m.texture, strike);
+    const uint32_t surface = (SceneAccess<SMEM>::kLean || is_plane || m.texture < 0) ? m.rgb : texture_colour(sc.g, m.texture, strike);
     const uint32_t nc = darken(m.albedo, combine(colour, surface));
 
     // ---- the bounce's first RNG block, for every style that draws ----
@@ -1118,7 +1123,7 @@ RTFS_HD bool path_begin(PathState &p, const DevCamera &cam, uint32_t k0, uint32_
 }
 // the part of a step that follows hitObject: Reflection, bounce count (Scene.fs:102-114).
 // Returns true when the path is finished; `result` is then its Pixel.
-template <bool SMEM>
+template <int SMEM>
 RTFS_HD bool path_after_hit(PathState &p, const SceneAccess<SMEM> &sc, const Hit &h, int max_count, uint32_t &result) {
     if (h.prim == kNoPrim) { // the ray goes off into the distance
         result = kBlack;
@@ -1144,7 +1149,7 @@ RTFS_HD bool path_after_hit(PathState &p, const SceneAccess<SMEM> &sc, const Hit
     return false;
 }
 // one whole step: hitObject + Reflection; returns true when the path is finished
-template <bool SMEM, bool COUNT, class Stack, bool WIDE = false>
+template <int SMEM, bool COUNT, class Stack, bool WIDE = false>
 RTFS_HD bool path_step(PathState &p, const SceneAccess<SMEM> &sc, int max_count, uint32_t &result, TraversalCounters &cn, unsigned lanes,
                        Stack &stack) {
     Hit h = closest_hit_from<SMEM, COUNT, Stack, WIDE>(sc, p.o, p.d, p.last, cn, lanes, stack);

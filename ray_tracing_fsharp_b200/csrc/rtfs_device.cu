@@ -244,6 +244,10 @@ int device_scene_upload(RtScene *scene) {
     ds->g.n_unbounded = int32_t(L.unbounded.size());
     ds->g.n_tex = int32_t(scene->textures.size());
     ds->max_depth = L.max_depth;
+    // lean: nothing in this scene needs the FP64 evaluation of an unbounded object or a texture lookup (SceneAccess, rtfs_core.cuh)
+    ds->lean = true;
+    for (const DUnbounded &u : L.unbounded) ds->lean = ds->lean && u.fp32 == 1;
+    for (const DMaterial &m : L.materials) ds->lean = ds->lean && m.texture < 0;
     if (!L.wide_nodes.empty()) return device_scene_ensure_wide(scene); // built at creation for big scenes
     return RT_OK;
 }
@@ -309,7 +313,7 @@ int device_scene_ensure_reference(RtScene *scene) {
 // ---------------------------------------------------------------------------------------------------
 // render kernels
 // ---------------------------------------------------------------------------------------------------
-template <bool SMEM>
+template <int SMEM>
 __device__ __forceinline__ SceneAccess<SMEM> stage_scene(const FrameParams &fp) {
     SceneAccess<SMEM> sc;
     sc.g = fp.g;
@@ -368,7 +372,7 @@ __device__ __forceinline__ void flush_counters(unsigned long long *counters, uin
 //                  remaining sample indices (Scene.fs:191-192).
 // A warp issues one instruction every ~7.6 cycles whatever the load, so the kernel ends one whole item after the
 // work runs out: hence chunks of decreasing length, the last ones a single sample (see build_chunks).
-template <bool PROBE, bool SMEM, bool COUNT, bool SSTACK, bool WIDE>
+template <bool PROBE, int SMEM, bool COUNT, bool SSTACK, bool WIDE>
 __global__ void __launch_bounds__(block_threads(SMEM), blocks_per_sm(SMEM)) render_kernel(const FrameParams fp) {
     const SceneAccess<SMEM> sc = stage_scene<SMEM>(fp);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -605,23 +609,24 @@ struct LaunchPlan {
 };
 
 typedef void (*RenderKernelFn)(const FrameParams);
-template <bool PROBE, bool SMEM, bool SSTACK, bool WIDE>
+template <bool PROBE, int SMEM, bool SSTACK, bool WIDE>
 static RenderKernelFn pick_count(bool count) {
     return count ? render_kernel<PROBE, SMEM, true, SSTACK, WIDE> : render_kernel<PROBE, SMEM, false, SSTACK, WIDE>;
 }
 template <bool PROBE>
 static RenderKernelFn pick_global(bool sstack, bool wide, bool count) { // the scene is read from global memory
-    if (wide) return sstack ? pick_count<PROBE, false, true, true>(count) : pick_count<PROBE, false, false, true>(count);
-    return sstack ? pick_count<PROBE, false, true, false>(count) : pick_count<PROBE, false, false, false>(count);
+    if (wide) return sstack ? pick_count<PROBE, 0, true, true>(count) : pick_count<PROBE, 0, false, true>(count);
+    return sstack ? pick_count<PROBE, 0, true, false>(count) : pick_count<PROBE, 0, false, false>(count);
 }
 template <bool PROBE>
 static RenderKernelFn pick_flow(bool smem, bool count) {
     if (smem) return count ? render_flow_kernel<PROBE, true, true> : render_flow_kernel<PROBE, true, false>;
     return count ? render_flow_kernel<PROBE, false, true> : render_flow_kernel<PROBE, false, false>;
 }
-static RenderKernelFn pick_kernel(bool probe, bool smem, bool count, bool sstack, bool wide) {
-    if (probe) return smem ? pick_count<true, true, false, false>(count) : pick_global<true>(sstack, wide, count);
-    return smem ? pick_count<false, true, false, false>(count) : pick_global<false>(sstack, wide, count);
+static RenderKernelFn pick_kernel(bool probe, bool smem, bool lean, bool count, bool sstack, bool wide) {
+    if (smem && lean) return probe ? pick_count<true, 2, false, false>(count) : pick_count<false, 2, false, false>(count);
+    if (probe) return smem ? pick_count<true, 1, false, false>(count) : pick_global<true>(sstack, wide, count);
+    return smem ? pick_count<false, 1, false, false>(count) : pick_global<false>(sstack, wide, count);
 }
 
 // does a block with `bytes` of dynamic shared memory leave room for `per_sm` of its kind on an SM (1 KB reserved per block)
@@ -667,7 +672,7 @@ static int plan_launch(DeviceScene *ds, FrameParams &fp, bool probe, bool count,
     }
     fp.stack_levels = int32_t(stack_q * 16 / (size_t(plan.threads) * 4));
     plan.smem_bytes = (used_q + (sstack ? stack_q : 0)) * 16;
-    fn = flow ? (probe ? pick_flow<true>(smem, count) : pick_flow<false>(smem, count)) : pick_kernel(probe, smem, count, sstack, wide);
+    fn = flow ? (probe ? pick_flow<true>(smem, count) : pick_flow<false>(smem, count)) : pick_kernel(probe, smem, ds->lean && !(fp.opt_flags & RT_FLAG_NO_LEAN), count, sstack, wide);
     { // The dynamic shared-memory limit of a kernel is a per-function, per-device setting: it is only ever RAISED here
       // (to the largest size any scene has asked for), and the occupancy of a (kernel, size, device) triple is asked once.
         struct Known {

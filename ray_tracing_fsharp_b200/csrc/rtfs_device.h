@@ -80,6 +80,7 @@ struct DeviceScene {
     std::vector<PooledTexture> images; // image textures borrowed from the pool
     size_t bytes = 0;
     int32_t max_depth = 0; // depth of the tree: the walk's stack never holds more entries
+    bool lean = false;     // no FP64 unbounded object, no texture index: the staged kernels have a variant without that code
     DeviceWorkspace *ws = nullptr;
 };
 

@@ -199,6 +199,25 @@ def test_flow_and_lockstep_schedules_agree_bit_for_bit(which):
         assert np.array_equal(s1, s2), (which, spp)
 
 
+@pytest.mark.parametrize("which", ["reduced", "C1", "C2"])
+def test_lean_kernel_agrees_bit_for_bit(which):
+    """Scenes whose unbounded objects are all cleared for FP32 and whose materials carry no texture index run a kernel compiled
+    without the FP64 evaluations and the texture lookup (SceneAccess<2>, DeviceScene::lean); RT_FLAG_NO_LEAN keeps the full
+    kernel.  Same sums, same counts, adaptive and not, with the counters on."""
+    spec = small_random_spheres() if which == "reduced" else _small(which, 48, 27, 24)
+    osc, dsc, cam = scene_pair(spec)
+    mw, mh = spec.max_width_coord, spec.max_height_coord
+    for adaptive in (True, False):
+        for extra in (0, abi.RT_FLAG_COUNTERS):
+            _, sa, sta = dsc.render(cam, mw, mh, seed=53, adaptive=adaptive, want_sums=True, flags=extra)
+            sa = sa.copy()
+            _, sb, stb = dsc.render(cam, mw, mh, seed=53, adaptive=adaptive, want_sums=True, flags=extra | abi.RT_FLAG_NO_LEAN)
+            assert np.array_equal(sa, sb), (which, adaptive, extra, int((sa != sb).any(2).sum()))
+            assert int(sta.rays) == int(stb.rays) and int(sta.paths) == int(stb.paths)
+            if extra:
+                assert int(sta.box_tests) == int(stb.box_tests) and int(sta.prim_tests) == int(stb.prim_tests)
+
+
 def test_more_samples_than_one_main_launch_covers():
     """A work item holds at most 256 samples of a pixel (its red and green sums share a word) and one main-phase launch at
     most 160 x 256 sample indices of a rank: a frame with more is several launches.  3 x 3 pixels at 41 500 spp (adaptive off
